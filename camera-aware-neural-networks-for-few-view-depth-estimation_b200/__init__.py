@@ -1,0 +1,286 @@
+"""B200-native camera-aware depth-loss kernels: Python access to the C ABI.
+
+The product is ``csrc/libcadl.so`` (hand-written sm_100a kernels behind ``include/cadl.h``) and the
+C++ drop-in headers under ``host/``.  This package is only the thin ctypes layer that tests, the
+benchmark and ``__graft_entry__`` use to reach them; PyTorch supplies device memory and streams.
+
+There is no CPU implementation: every entry point raises if the library is missing or a tensor is
+not on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REPO_ROOT = os.path.dirname(_HERE)
+LIBCADL_PATH = os.path.join(_HERE, "csrc", "libcadl.so")
+LIBHOST_PATH = os.path.join(_HERE, "host", "libcadl_host.so")
+
+TERM_SI, TERM_GRAD, TERM_SMOOTH, TERM_REPROJ, TERM_ALL = 1, 2, 4, 8, 15
+METRICS_EVAL, METRICS_TRAIN = 1, 2
+
+EVAL_KEYS = ("abs_rel", "sq_rel", "rmse", "rmse_log", "mae", "log10",
+             "delta_1.25", "delta_1.25^2", "delta_1.25^3",
+             "num_valid_pixels", "mean_pred_depth", "mean_gt_depth")
+TRAIN_KEYS = ("abs_rel", "sq_rel", "rmse", "rmse_log", "a1", "a2", "a3")
+
+
+class CadlParams(C.Structure):
+    """Mirror of ``cadl_params`` (include/cadl.h)."""
+    _fields_ = [
+        ("terms", C.c_uint32), ("metrics", C.c_uint32),
+        ("w_si", C.c_float), ("w_grad", C.c_float), ("w_smooth", C.c_float), ("w_reproj", C.c_float),
+        ("si_lambda", C.c_float),
+        ("eps_si", C.c_float), ("eps_grad", C.c_float), ("eps_smooth", C.c_float), ("eps_reproj", C.c_float),
+        ("num_scales", C.c_int32), ("k_batched", C.c_int32),
+        ("min_depth", C.c_float), ("max_depth", C.c_float),
+        ("upstream", C.c_float),
+        ("global_B", C.c_int32),
+    ]
+
+
+class CadlResults(C.Structure):
+    """Mirror of ``cadl_results`` (include/cadl.h)."""
+    _fields_ = [
+        ("loss_total", C.c_float), ("loss_si", C.c_float), ("loss_grad", C.c_float),
+        ("loss_smooth", C.c_float), ("loss_reproj", C.c_float), ("_pad0", C.c_float * 3),
+        ("d_total", C.c_double), ("d_si", C.c_double), ("d_grad", C.c_double),
+        ("d_smooth", C.c_double), ("d_reproj", C.c_double),
+        ("n_si", C.c_int64), ("n_reproj", C.c_int64),
+        ("eval", C.c_float * 12), ("eval_counts", C.c_int64 * 4),
+        ("train", C.c_float * 8), ("train_counts", C.c_int64 * 4),
+    ]
+
+
+# every symbol include/cadl.h declares (tests/test_abi.py checks the .so exports each one)
+ABI_SYMBOLS = (
+    "cadl_default_params", "cadl_version", "cadl_sizeof_params", "cadl_sizeof_results", "cadl_error_string", "cadl_workspace_bytes", "cadl_workspace_init",
+    "cadl_stack_fwd_bwd", "cadl_stack_reduce", "cadl_stack_grad", "cadl_stats_offset", "cadl_stats_count",
+    "cadl_si_fwd_bwd", "cadl_gradmatch_fwd_bwd", "cadl_smooth_fwd_bwd", "cadl_reproj_fwd_bwd",
+    "cadl_scale_grad", "cadl_metrics", "cadl_rays_from_K", "cadl_photometric_fwd_bwd",
+)
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libcadl.so (built by ``__graft_entry__.build()``); fail loudly if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIBCADL_PATH):
+        raise RuntimeError(
+            f"cadl: {LIBCADL_PATH} is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+            " (nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(LIBCADL_PATH)
+    vp, f32p, u8p = C.c_void_p, C.c_void_p, C.c_void_p
+    L.cadl_default_params.argtypes = [C.POINTER(CadlParams)]
+    L.cadl_default_params.restype = None
+    L.cadl_version.restype = C.c_int
+    L.cadl_sizeof_params.restype = C.c_size_t
+    L.cadl_sizeof_results.restype = C.c_size_t
+    L.cadl_error_string.argtypes = [C.c_int]
+    L.cadl_error_string.restype = C.c_char_p
+    L.cadl_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.cadl_workspace_bytes.restype = C.c_size_t
+    L.cadl_workspace_init.argtypes = [vp, C.c_size_t, vp]
+    L.cadl_stats_offset.restype = C.c_size_t
+    L.cadl_stats_count.restype = C.c_int
+    L.cadl_stack_fwd_bwd.argtypes = [f32p, f32p, f32p, f32p, u8p, C.c_int, C.c_int, C.c_int,
+                                     C.POINTER(CadlParams), f32p, vp, vp, C.c_size_t, vp]
+    L.cadl_stack_reduce.argtypes = [f32p, f32p, u8p, C.c_int, C.c_int, C.c_int, C.POINTER(CadlParams),
+                                    vp, C.c_size_t, vp]
+    L.cadl_stack_grad.argtypes = L.cadl_stack_fwd_bwd.argtypes
+    L.cadl_si_fwd_bwd.argtypes = [f32p, f32p, u8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                  f32p, vp, vp, C.c_size_t, vp]
+    L.cadl_gradmatch_fwd_bwd.argtypes = [f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                         f32p, vp, vp, C.c_size_t, vp]
+    L.cadl_smooth_fwd_bwd.argtypes = [f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                      f32p, vp, vp, C.c_size_t, vp]
+    L.cadl_reproj_fwd_bwd.argtypes = [f32p, f32p, f32p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_float,
+                                      C.c_float, f32p, vp, vp, C.c_size_t, vp]
+    L.cadl_scale_grad.argtypes = [f32p, f32p, f32p, C.c_size_t, vp]
+    L.cadl_metrics.argtypes = [f32p, f32p, u8p, C.c_size_t, C.c_uint32, C.c_float, C.c_float, vp, vp,
+                               C.c_size_t, vp]
+    L.cadl_rays_from_K.argtypes = [f32p, C.c_int, f32p, C.c_int, C.c_int, C.c_int, C.c_int, f32p, vp]
+    L.cadl_photometric_fwd_bwd.argtypes = [f32p, f32p, C.c_int, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int,
+                                           C.c_float, C.c_float, f32p, vp, vp, C.c_size_t, vp]
+    for name in ABI_SYMBOLS:
+        getattr(L, name)   # AttributeError here = the .so does not export what include/cadl.h declares
+    if L.cadl_sizeof_params() != C.sizeof(CadlParams) or L.cadl_sizeof_results() != C.sizeof(CadlResults):
+        raise RuntimeError("cadl: ctypes mirrors of cadl_params/cadl_results disagree with libcadl.so")
+    _lib = L
+    return L
+
+
+class CadlError(RuntimeError):
+    pass
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise CadlError(f"{what}: {lib().cadl_error_string(rc).decode()} (code {rc})")
+
+
+def default_params(**over) -> CadlParams:
+    p = CadlParams()
+    lib().cadl_default_params(C.byref(p))
+    for k, v in over.items():
+        setattr(p, k, v)
+    return p
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise CadlError("cadl: tensors must live on a CUDA device (no CPU fallback)")
+
+
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+class Workspace:
+    """Caller-owned scratch for one (B,H,W) problem on one stream; zeroed once, left clean by every call."""
+
+    def __init__(self, B: int, H: int, W: int, device):
+        self.shape = (B, H, W)
+        self.bytes = int(lib().cadl_workspace_bytes(B, H, W))
+        if self.bytes == 0:
+            raise CadlError("cadl: bad problem size")
+        self.buf = torch.zeros(self.bytes, dtype=torch.uint8, device=device)
+        self.results = torch.zeros(C.sizeof(CadlResults), dtype=torch.uint8, device=device)
+
+    def stats_view(self) -> torch.Tensor:
+        """The exchangeable fp64 statistics vector (all-reduce it between reduce and grad in mode B)."""
+        off = int(lib().cadl_stats_offset())
+        n = int(lib().cadl_stats_count())
+        return self.buf[off:off + 8 * n].view(torch.float64)
+
+    def read_results(self) -> CadlResults:
+        host = self.results.cpu().numpy().tobytes()
+        return CadlResults.from_buffer_copy(host)
+
+
+def results_dict(r: CadlResults) -> Dict[str, object]:
+    return {
+        "loss_total": r.loss_total, "si_loss": r.loss_si, "grad_loss": r.loss_grad,
+        "smooth_loss": r.loss_smooth, "reproj_loss": r.loss_reproj,
+        "d_total": r.d_total, "d_si": r.d_si, "d_grad": r.d_grad, "d_smooth": r.d_smooth, "d_reproj": r.d_reproj,
+        "n_si": r.n_si, "n_reproj": r.n_reproj,
+        "eval": {k: r.eval[i] for i, k in enumerate(EVAL_KEYS)},
+        "eval_counts": [int(x) for x in r.eval_counts],
+        "train": {k: r.train[i] for i, k in enumerate(TRAIN_KEYS)},
+        "train_counts": [int(x) for x in r.train_counts],
+    }
+
+
+def stack_fwd_bwd(pred, gt, rgb, K, mask=None, params: Optional[CadlParams] = None,
+                  grad: Optional[torch.Tensor] = None, want_grad: bool = True,
+                  ws: Optional[Workspace] = None) -> Workspace:
+    """Launch the fused forward+backward (asynchronous).  Results stay on the device in ``ws.results``;
+    the gradient is written to ``grad`` (allocated as ``ws.grad`` if not given)."""
+    _require_cuda(pred, gt, rgb, K, mask, grad)
+    B, _, H, W = pred.shape
+    p = params if params is not None else default_params()
+    if K is not None:
+        p.k_batched = 1 if K.dim() == 3 else 0
+    if ws is None:
+        ws = Workspace(B, H, W, pred.device)
+    if want_grad and grad is None:
+        grad = torch.empty_like(pred)
+    ws.grad = grad if want_grad else None
+    with torch.cuda.device(pred.device):
+        rc = lib().cadl_stack_fwd_bwd(_ptr(pred), _ptr(gt), _ptr(rgb), _ptr(K), _ptr(mask), B, H, W, C.byref(p),
+                                      _ptr(ws.grad), _ptr(ws.results), _ptr(ws.buf), ws.bytes, _stream(pred))
+    _check(rc, "cadl_stack_fwd_bwd")
+    return ws
+
+
+def stack_reduce(pred, gt, mask, params: CadlParams, ws: Workspace):
+    _require_cuda(pred, gt, mask)
+    B, _, H, W = pred.shape
+    with torch.cuda.device(pred.device):
+        rc = lib().cadl_stack_reduce(_ptr(pred), _ptr(gt), _ptr(mask), B, H, W, C.byref(params), _ptr(ws.buf),
+                                     ws.bytes, _stream(pred))
+    _check(rc, "cadl_stack_reduce")
+
+
+def stack_grad(pred, gt, rgb, K, mask, params: CadlParams, grad, ws: Workspace):
+    _require_cuda(pred, gt, rgb, K, mask, grad)
+    B, _, H, W = pred.shape
+    ws.grad = grad
+    with torch.cuda.device(pred.device):
+        rc = lib().cadl_stack_grad(_ptr(pred), _ptr(gt), _ptr(rgb), _ptr(K), _ptr(mask), B, H, W, C.byref(params),
+                                   _ptr(grad), _ptr(ws.results), _ptr(ws.buf), ws.bytes, _stream(pred))
+    _check(rc, "cadl_stack_grad")
+
+
+def metrics(pred, gt, mask=None, which: int = METRICS_EVAL | METRICS_TRAIN, min_depth: float = 0.1,
+            max_depth: float = 10.0, ws: Optional[Workspace] = None) -> Workspace:
+    _require_cuda(pred, gt, mask)
+    n = pred.numel()
+    if ws is None:
+        ws = Workspace(1, 1, n, pred.device)
+    with torch.cuda.device(pred.device):
+        rc = lib().cadl_metrics(_ptr(pred), _ptr(gt), _ptr(mask), n, which, min_depth, max_depth, _ptr(ws.results),
+                                _ptr(ws.buf), ws.bytes, _stream(pred))
+    _check(rc, "cadl_metrics")
+    return ws
+
+
+def scale_grad(grad_in, upstream_dev, grad_out):
+    _require_cuda(grad_in, upstream_dev, grad_out)
+    with torch.cuda.device(grad_in.device):
+        rc = lib().cadl_scale_grad(_ptr(grad_in), _ptr(upstream_dev), _ptr(grad_out), grad_in.numel(),
+                                   _stream(grad_in))
+    _check(rc, "cadl_scale_grad")
+
+
+def rays_from_K(K, H: int, W: int, layout: int = 1, pose=None) -> torch.Tensor:
+    """Unit ray directions from intrinsics: layout 0 -> (B,H*W,3), layout 1 -> (B,3,H,W)."""
+    _require_cuda(K, pose)
+    kb = 1 if K.dim() == 3 else 0
+    B = K.shape[0] if kb else (pose.shape[0] if pose is not None else 1)
+    out = torch.empty((B, H * W, 3) if layout == 0 else (B, 3, H, W), dtype=torch.float32, device=K.device)
+    with torch.cuda.device(K.device):
+        rc = lib().cadl_rays_from_K(_ptr(K), kb, _ptr(pose), B, H, W, layout, _ptr(out), _stream(K))
+    _check(rc, "cadl_rays_from_K")
+    return out
+
+
+def photometric_fwd_bwd(pred, K, T, source, target, eps: float = 1e-6, upstream: float = 1.0,
+                        want_grad: bool = True, ws: Optional[Workspace] = None) -> Workspace:
+    _require_cuda(pred, K, T, source, target)
+    B, _, H, W = pred.shape
+    if ws is None:
+        ws = Workspace(B, H, W, pred.device)
+    ws.grad = torch.empty_like(pred) if want_grad else None
+    kb = 1 if K.dim() == 3 else 0
+    with torch.cuda.device(pred.device):
+        rc = lib().cadl_photometric_fwd_bwd(_ptr(pred), _ptr(K), kb, _ptr(T), _ptr(source), _ptr(target), B, H, W,
+                                            eps, upstream, _ptr(ws.grad), _ptr(ws.results), _ptr(ws.buf), ws.bytes,
+                                            _stream(pred))
+    _check(rc, "cadl_photometric_fwd_bwd")
+    return ws
+
+
+from .harness import StepHarness, StepCfg  # noqa: E402
+from . import synth  # noqa: E402
+from .rays_io import save_ray_directions, load_ray_directions  # noqa: E402
+
+
+def host_harness() -> StepHarness:
+    """The drop-in C++ classes (host/loss/depth_loss.h ...) behind the trainer-shaped C harness."""
+    if not os.path.exists(LIBHOST_PATH):
+        raise RuntimeError(f"cadl: {LIBHOST_PATH} is missing -- run __graft_entry__.build()")
+    lib()  # libcadl.so first, so the host library resolves against the in-tree build
+    return StepHarness(LIBHOST_PATH)

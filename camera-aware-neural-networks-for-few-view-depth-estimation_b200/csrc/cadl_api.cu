@@ -1,0 +1,377 @@
+// cadl C ABI (include/cadl.h): argument checks, workspace carving, kernel dispatch.
+// Built only for sm_100a; there is no host/CPU implementation behind these entry points.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "cadl.h"
+#include "cadl_common.cuh"
+#include "cadl_phase_a.cuh"
+#include "cadl_phase_b.cuh"
+#include "cadl_rays.cuh"
+#include "cadl_photometric.cuh"
+
+using namespace cadl;
+
+namespace {
+
+inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? CADL_OK : CADL_ERR_CUDA + (int)e; }
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+thread_local char g_err_detail[256];
+
+struct Ws {
+    WsLayout L;
+    char* base;
+    WsHeader* hdr() const { return reinterpret_cast<WsHeader*>(base + L.header); }
+    double* stats() const { return reinterpret_cast<double*>(base + L.stats); }
+    double* img_psum() const { return reinterpret_cast<double*>(base + L.img_psum); }
+    double* a_part() const { return reinterpret_cast<double*>(base + L.a_part); }
+    double* b_part() const { return reinterpret_cast<double*>(base + L.b_part); }
+    double* img_sm() const { return reinterpret_cast<double*>(base + L.img_sm); }
+    float* img_off() const { return reinterpret_cast<float*>(base + L.img_off); }
+};
+
+constexpr int kPointBlocks = 148 * 8;
+
+WsLayout layout_for(int B, int H, int W) {
+    WsLayout L = ws_layout(B, H, W);
+    return L;
+}
+
+int check_common(int B, int H, int W, const void* ws, size_t ws_bytes) {
+    if (B < 1 || H < 1 || W < 1) return CADL_ERR_SHAPE;
+    if ((long long)B * H * W > 0x7fffffffLL) return CADL_ERR_SHAPE;
+    if (!ws) return CADL_ERR_NULL;
+    if (!aligned(ws, 256)) return CADL_ERR_WORKSPACE;
+    if (ws_bytes < cadl_workspace_bytes(B, H, W)) return CADL_ERR_WORKSPACE;
+    return CADL_OK;
+}
+
+uint32_t phase_a_flags(const cadl_params& p) {
+    uint32_t f = 0;
+    if (p.terms & CADL_TERM_SI) f |= FA_SI;
+    if (p.terms & CADL_TERM_REPROJ) f |= FA_RP;
+    if (p.terms & CADL_TERM_SMOOTH) f |= FA_PSUM;
+    if (p.metrics & CADL_METRICS_EVAL) f |= FA_EV;
+    if (p.metrics & CADL_METRICS_TRAIN) f |= FA_TR;
+    return f;
+}
+
+template <int F>
+cudaError_t launch_a(const PhaseAArgs& a, dim3 grid, cudaStream_t st) {
+    phase_a_kernel<F><<<grid, kThreadsA, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t dispatch_a(uint32_t f, const PhaseAArgs& a, dim3 grid, cudaStream_t st) {
+    switch (f) {
+#define CADL_A(n) case n: return launch_a<n>(a, grid, st);
+        CADL_A(1) CADL_A(2) CADL_A(3) CADL_A(4) CADL_A(5) CADL_A(6) CADL_A(7) CADL_A(8) CADL_A(9)
+        CADL_A(10) CADL_A(11) CADL_A(12) CADL_A(13) CADL_A(14) CADL_A(15) CADL_A(16) CADL_A(17)
+        CADL_A(18) CADL_A(19) CADL_A(20) CADL_A(21) CADL_A(22) CADL_A(23) CADL_A(24) CADL_A(25)
+        CADL_A(26) CADL_A(27) CADL_A(28) CADL_A(29) CADL_A(30) CADL_A(31)
+#undef CADL_A
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+template <int F>
+cudaError_t launch_tile(const PhaseBArgs& a, cudaStream_t st) {
+    static bool configured = false;   // per-process; attribute is per-function, idempotent
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(phase_b_tile_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)kTileSmemBytes);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    phase_b_tile_kernel<F><<<a.b_rows, kThreadsB, kTileSmemBytes, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int F>
+cudaError_t launch_point(const PhaseBArgs& a, cudaStream_t st) {
+    phase_b_point_kernel<F><<<a.b_rows, kThreadsB, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+int run_reduce(const float* pred, const float* gt, const uint8_t* mask, int B, int H, int W,
+               const cadl_params& p, const Ws& ws, cudaStream_t st) {
+    uint32_t f = phase_a_flags(p);
+    if (f == 0) return CADL_OK;
+    const bool need_p = f & (FA_SI | FA_PSUM | FA_EV | FA_TR);
+    const bool need_g = f & (FA_SI | FA_RP | FA_EV | FA_TR);
+    if ((need_p && !pred) || (need_g && !gt)) return CADL_ERR_NULL;
+    PhaseAArgs a{};
+    a.pred = pred; a.gt = gt; a.mask = mask;
+    a.B = B; a.HW = H * W;
+    a.blocks_per_img = ws.L.a_blocks_per_img;
+    a.vec_ok = ((H * W) % 4 == 0) && (!pred || aligned(pred, 16)) && (!gt || aligned(gt, 16)) &&
+               (!mask || aligned(mask, 4));
+    a.eps_si = p.eps_si; a.eps_rp = p.eps_reproj; a.min_d = p.min_depth; a.max_d = p.max_depth;
+    a.hdr = ws.hdr(); a.stats = ws.stats(); a.img_psum = ws.img_psum(); a.a_part = ws.a_part();
+    dim3 grid(a.blocks_per_img, B);
+    return cuda_rc(dispatch_a(f, a, grid, st));
+}
+
+int run_grad(const float* pred, const float* gt, const float* rgb, const float* K, const uint8_t* mask,
+             int B, int H, int W, const cadl_params& p, float* grad, cadl_results* results, const Ws& ws,
+             cudaStream_t st) {
+    if (!results) return CADL_ERR_NULL;
+    const uint32_t t = p.terms & CADL_TERM_ALL;
+    if (t == 0) {
+        if (p.metrics) {
+            metrics_finalize_kernel<<<1, 32, 0, st>>>(ws.stats(), p.metrics, results);
+            return cuda_rc(cudaGetLastError());
+        }
+        return CADL_OK;
+    }
+    if (!pred) return CADL_ERR_NULL;
+    if ((t & (CADL_TERM_SI | CADL_TERM_GRAD | CADL_TERM_REPROJ)) && !gt) return CADL_ERR_NULL;
+    if ((t & CADL_TERM_SMOOTH) && !rgb) return CADL_ERR_NULL;
+    if ((t & CADL_TERM_REPROJ) && !K) return CADL_ERR_NULL;
+    if (t & CADL_TERM_GRAD) {
+        if (p.num_scales < 1 || p.num_scales > CADL_MAX_SCALES) return CADL_ERR_UNSUPPORTED;
+        // avg_pool2d needs at least one output cell at the coarsest scale (torch raises otherwise)
+        if ((H >> (p.num_scales - 1)) < 1 || (W >> (p.num_scales - 1)) < 1) return CADL_ERR_SHAPE;
+    }
+    PhaseBArgs a{};
+    a.pred = pred; a.gt = gt; a.rgb = rgb; a.K = K; a.mask = mask; a.grad = grad;
+    a.B = B; a.H = H; a.W = W;
+    a.tiles_x = (W + TW - 1) / TW; a.tiles_y = (H + TH - 1) / TH;
+    a.vec_ok = (W % 4 == 0) && aligned(pred, 16) && (!gt || aligned(gt, 16)) && (!rgb || aligned(rgb, 16)) &&
+               (!grad || aligned(grad, 16)) && (!mask || aligned(mask, 4));
+    a.num_scales = p.num_scales; a.k_batched = p.k_batched;
+    a.global_B = p.global_B > 0 ? p.global_B : B;
+    a.terms = t; a.metrics = p.metrics;
+    a.w_si = p.w_si; a.w_grad = p.w_grad; a.w_smooth = p.w_smooth; a.w_rp = p.w_reproj;
+    a.lambda = p.si_lambda;
+    a.eps_si = p.eps_si; a.eps_grad = p.eps_grad; a.eps_smooth = p.eps_smooth; a.eps_rp = p.eps_reproj;
+    a.upstream = p.upstream;
+    a.stats = ws.stats(); a.img_psum = ws.img_psum(); a.b_part = ws.b_part();
+    a.hdr = ws.hdr(); a.img_sm = ws.img_sm(); a.img_off = ws.img_off();
+    a.results = results;
+
+    cudaError_t e = cudaSuccess;
+    if ((t & (CADL_TERM_GRAD | CADL_TERM_SMOOTH)) == 0) {
+        a.b_rows = kPointBlocks;
+        switch (t) {
+            case CADL_TERM_SI: e = launch_point<FB_SI>(a, st); break;
+            case CADL_TERM_REPROJ: e = launch_point<FB_RP>(a, st); break;
+            case CADL_TERM_SI | CADL_TERM_REPROJ: e = launch_point<FB_SI | FB_RP>(a, st); break;
+            default: return CADL_ERR_UNSUPPORTED;
+        }
+        return cuda_rc(e);
+    }
+    a.b_rows = ws.L.b_tiles;
+    switch (t) {
+        case CADL_TERM_ALL: e = launch_tile<15>(a, st); break;                           // forwardWithIntrinsics
+        case CADL_TERM_SI | CADL_TERM_GRAD | CADL_TERM_SMOOTH: e = launch_tile<7>(a, st); break;  // forward
+        case CADL_TERM_GRAD: e = launch_tile<FB_GRAD>(a, st); break;
+        case CADL_TERM_SMOOTH: e = launch_tile<FB_SMOOTH>(a, st); break;
+        default: return CADL_ERR_UNSUPPORTED;
+    }
+    if (e != cudaSuccess) return cuda_rc(e);
+    if ((t & CADL_TERM_SMOOTH) && grad) {
+        const int HW = H * W;
+        const int vec = (HW % 4 == 0) && aligned(grad, 16);
+        int bx = (HW / 4 + 255) / 256;
+        int cap = (148 * 8 + B - 1) / B;
+        if (bx > cap) bx = cap;
+        if (bx < 1) bx = 1;
+        smooth_offset_kernel<<<dim3(bx, B), 256, 0, st>>>(grad, ws.img_off(), HW, vec);
+        e = cudaGetLastError();
+    }
+    return cuda_rc(e);
+}
+
+}  // namespace
+
+extern "C" {
+
+void cadl_default_params(cadl_params* p) {
+    memset(p, 0, sizeof(*p));
+    p->terms = CADL_TERM_ALL;
+    p->metrics = 0;
+    p->w_si = 1.0f; p->w_grad = 0.1f; p->w_smooth = 0.001f; p->w_reproj = 0.01f;   // depth_loss.h:368-371
+    p->si_lambda = 0.5f;                                                            // :22
+    p->eps_si = p->eps_grad = p->eps_smooth = p->eps_reproj = 1e-6f;                // :22,84,180,257
+    p->num_scales = 4;                                                              // :84
+    p->k_batched = 1;
+    p->min_depth = 0.1f; p->max_depth = 10.0f;                                      // depth_metrics.h:44-45
+    p->upstream = 1.0f;
+    p->global_B = 0;
+}
+
+int cadl_version(void) { return CADL_VERSION; }
+size_t cadl_sizeof_params(void) { return sizeof(cadl_params); }
+size_t cadl_sizeof_results(void) { return sizeof(cadl_results); }
+
+const char* cadl_error_string(int code) {
+    switch (code) {
+        case CADL_OK: return "ok";
+        case CADL_ERR_NULL: return "cadl: a required pointer is NULL";
+        case CADL_ERR_SHAPE: return "cadl: B/H/W out of range for the requested terms";
+        case CADL_ERR_WORKSPACE: return "cadl: workspace too small or not 256-byte aligned";
+        case CADL_ERR_UNSUPPORTED: return "cadl: unsupported term combination or num_scales";
+        case CADL_ERR_ALIGN: return "cadl: data pointer not 4-byte aligned";
+        default: break;
+    }
+    if (code >= CADL_ERR_CUDA) {
+        snprintf(g_err_detail, sizeof(g_err_detail), "cadl: CUDA error %d: %s", code - CADL_ERR_CUDA,
+                 cudaGetErrorString((cudaError_t)(code - CADL_ERR_CUDA)));
+        return g_err_detail;
+    }
+    return "cadl: unknown error";
+}
+
+size_t cadl_workspace_bytes(int B, int H, int W) {
+    if (B < 1 || H < 1 || W < 1) return 0;
+    WsLayout L = layout_for(B, H, W);
+    // the pointwise kernel writes kPointBlocks partial rows
+    size_t need_b = sizeof(double) * (size_t)kPointBlocks * BF_COUNT;
+    size_t have_b = L.img_sm - L.b_part;
+    size_t extra = need_b > have_b ? align_up(need_b - have_b, 256) : 0;
+    return L.total + extra + 256;
+}
+
+static Ws make_ws(void* workspace, int B, int H, int W) {
+    Ws ws;
+    ws.L = layout_for(B, H, W);
+    size_t need_b = sizeof(double) * (size_t)kPointBlocks * BF_COUNT;
+    size_t have_b = ws.L.img_sm - ws.L.b_part;
+    if (need_b > have_b) {
+        size_t extra = align_up(need_b - have_b, 256);
+        ws.L.img_sm += extra; ws.L.img_off += extra; ws.L.total += extra;
+    }
+    ws.base = static_cast<char*>(workspace);
+    return ws;
+}
+
+int cadl_workspace_init(void* workspace, size_t bytes, cadl_stream_t stream) {
+    if (!workspace) return CADL_ERR_NULL;
+    return cuda_rc(cudaMemsetAsync(workspace, 0, bytes, (cudaStream_t)stream));
+}
+
+size_t cadl_stats_offset(void) { return align_up(sizeof(WsHeader), 256); }
+int cadl_stats_count(void) { return ST_COUNT; }
+
+int cadl_stack_reduce(const float* pred, const float* gt, const uint8_t* mask, int B, int H, int W,
+                      const cadl_params* params, void* workspace, size_t workspace_bytes, cadl_stream_t stream) {
+    if (!params) return CADL_ERR_NULL;
+    int rc = check_common(B, H, W, workspace, workspace_bytes);
+    if (rc) return rc;
+    Ws ws = make_ws(workspace, B, H, W);
+    return run_reduce(pred, gt, mask, B, H, W, *params, ws, (cudaStream_t)stream);
+}
+
+int cadl_stack_grad(const float* pred, const float* gt, const float* rgb, const float* K, const uint8_t* mask,
+                    int B, int H, int W, const cadl_params* params, float* grad_pred, cadl_results* results,
+                    void* workspace, size_t workspace_bytes, cadl_stream_t stream) {
+    if (!params) return CADL_ERR_NULL;
+    int rc = check_common(B, H, W, workspace, workspace_bytes);
+    if (rc) return rc;
+    Ws ws = make_ws(workspace, B, H, W);
+    return run_grad(pred, gt, rgb, K, mask, B, H, W, *params, grad_pred, results, ws, (cudaStream_t)stream);
+}
+
+int cadl_stack_fwd_bwd(const float* pred, const float* gt, const float* rgb, const float* K, const uint8_t* mask,
+                       int B, int H, int W, const cadl_params* params, float* grad_pred, cadl_results* results,
+                       void* workspace, size_t workspace_bytes, cadl_stream_t stream) {
+    if (!params) return CADL_ERR_NULL;
+    int rc = check_common(B, H, W, workspace, workspace_bytes);
+    if (rc) return rc;
+    Ws ws = make_ws(workspace, B, H, W);
+    rc = run_reduce(pred, gt, mask, B, H, W, *params, ws, (cudaStream_t)stream);
+    if (rc) return rc;
+    return run_grad(pred, gt, rgb, K, mask, B, H, W, *params, grad_pred, results, ws, (cudaStream_t)stream);
+}
+
+int cadl_si_fwd_bwd(const float* pred, const float* gt, const uint8_t* mask, int B, int H, int W, float lambda,
+                    float eps, float upstream, float* grad_pred, cadl_results* results, void* workspace,
+                    size_t workspace_bytes, cadl_stream_t stream) {
+    cadl_params p;
+    cadl_default_params(&p);
+    p.terms = CADL_TERM_SI; p.w_si = 1.0f; p.si_lambda = lambda; p.eps_si = eps; p.upstream = upstream;
+    return cadl_stack_fwd_bwd(pred, gt, nullptr, nullptr, mask, B, H, W, &p, grad_pred, results, workspace,
+                              workspace_bytes, stream);
+}
+
+int cadl_gradmatch_fwd_bwd(const float* pred, const float* gt, int B, int H, int W, int num_scales, float eps,
+                           float upstream, float* grad_pred, cadl_results* results, void* workspace,
+                           size_t workspace_bytes, cadl_stream_t stream) {
+    cadl_params p;
+    cadl_default_params(&p);
+    p.terms = CADL_TERM_GRAD; p.w_grad = 1.0f; p.num_scales = num_scales; p.eps_grad = eps; p.upstream = upstream;
+    return cadl_stack_fwd_bwd(pred, gt, nullptr, nullptr, nullptr, B, H, W, &p, grad_pred, results, workspace,
+                              workspace_bytes, stream);
+}
+
+int cadl_smooth_fwd_bwd(const float* pred, const float* rgb, int B, int H, int W, float eps, float upstream,
+                        float* grad_pred, cadl_results* results, void* workspace, size_t workspace_bytes,
+                        cadl_stream_t stream) {
+    cadl_params p;
+    cadl_default_params(&p);
+    p.terms = CADL_TERM_SMOOTH; p.w_smooth = 1.0f; p.eps_smooth = eps; p.upstream = upstream;
+    return cadl_stack_fwd_bwd(pred, nullptr, rgb, nullptr, nullptr, B, H, W, &p, grad_pred, results, workspace,
+                              workspace_bytes, stream);
+}
+
+int cadl_reproj_fwd_bwd(const float* pred, const float* gt, const float* K, int k_batched, const uint8_t* mask,
+                        int B, int H, int W, float eps, float upstream, float* grad_pred, cadl_results* results,
+                        void* workspace, size_t workspace_bytes, cadl_stream_t stream) {
+    cadl_params p;
+    cadl_default_params(&p);
+    p.terms = CADL_TERM_REPROJ; p.w_reproj = 1.0f; p.eps_reproj = eps; p.k_batched = k_batched;
+    p.upstream = upstream;
+    return cadl_stack_fwd_bwd(pred, gt, nullptr, K, mask, B, H, W, &p, grad_pred, results, workspace,
+                              workspace_bytes, stream);
+}
+
+int cadl_scale_grad(const float* grad_in, const float* upstream_dev, float* grad_out, size_t n,
+                    cadl_stream_t stream) {
+    if (!grad_in || !upstream_dev || !grad_out) return CADL_ERR_NULL;
+    if (n == 0) return CADL_OK;
+    const int vec = aligned(grad_in, 16) && aligned(grad_out, 16);
+    size_t blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    scale_grad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(grad_in, upstream_dev, grad_out, n, vec);
+    return cuda_rc(cudaGetLastError());
+}
+
+int cadl_metrics(const float* pred, const float* gt, const uint8_t* mask, size_t n, uint32_t which,
+                 float min_depth, float max_depth, cadl_results* results, void* workspace,
+                 size_t workspace_bytes, cadl_stream_t stream) {
+    if (!pred || !gt || !results) return CADL_ERR_NULL;
+    if (n == 0 || n > 0x7fffffffULL) return CADL_ERR_SHAPE;
+    if ((which & (CADL_METRICS_EVAL | CADL_METRICS_TRAIN)) == 0) return CADL_ERR_UNSUPPORTED;
+    // treated as one "image" of n values: H = 1, W = n
+    cadl_params p;
+    cadl_default_params(&p);
+    p.terms = 0; p.metrics = which; p.min_depth = min_depth; p.max_depth = max_depth;
+    return cadl_stack_fwd_bwd(pred, gt, nullptr, nullptr, mask, 1, 1, (int)n, &p, nullptr, results, workspace,
+                              workspace_bytes, stream);
+}
+
+int cadl_rays_from_K(const float* K, int k_batched, const float* pose, int B, int H, int W, int layout,
+                     float* out, cadl_stream_t stream) {
+    if (!K || !out) return CADL_ERR_NULL;
+    if (B < 1 || H < 1 || W < 1 || (layout != 0 && layout != 1)) return CADL_ERR_SHAPE;
+    return cuda_rc(launch_rays(K, k_batched, pose, B, H, W, layout, out, (cudaStream_t)stream));
+}
+
+int cadl_photometric_fwd_bwd(const float* pred, const float* K, int k_batched, const float* T,
+                             const float* source, const float* target, int B, int H, int W, float eps,
+                             float upstream, float* grad_pred, cadl_results* results, void* workspace,
+                             size_t workspace_bytes, cadl_stream_t stream) {
+    if (!pred || !K || !T || !source || !target || !results) return CADL_ERR_NULL;
+    int rc = check_common(B, H, W, workspace, workspace_bytes);
+    if (rc) return rc;
+    Ws ws = make_ws(workspace, B, H, W);
+    return cuda_rc(launch_photometric(pred, K, k_batched, T, source, target, B, H, W, eps, upstream, grad_pred,
+                                      results, ws.hdr(), ws.b_part(), kPointBlocks, ws.img_off(),
+                                      (cudaStream_t)stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,150 @@
+"""ctypes view of the trainer-shaped step harness (host/harness/step_harness.cpp).
+
+The same C surface is exported by two builds of that one source file:
+  * host/libcadl_host.so                -- the drop-in headers (product path, CUDA only);
+  * oracle/_ref/libcadl_refharness.so   -- the unmodified reference headers on LibTorch (oracle).
+All buffers crossing it are HOST numpy arrays; the harness moves them to its device the way the
+reference trainers do (src/training/production_trainer.h:192-194).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+TERM_NAMES = {0: "combined+K", 1: "si", 2: "grad", 3: "smooth", 4: "reproj", 5: "combined"}
+
+
+class _Cfg(C.Structure):
+    _fields_ = [("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("k_batched", C.c_int), ("device", C.c_int),
+                ("w_si", C.c_float), ("w_grad", C.c_float), ("w_smooth", C.c_float), ("w_reproj", C.c_float),
+                ("term", C.c_int), ("upstream", C.c_float)]
+
+
+@dataclass
+class StepCfg:
+    device: int = -1          # -1 CPU, >= 0 CUDA ordinal
+    term: int = 0             # see TERM_NAMES
+    w_si: float = 1.0
+    w_grad: float = 0.1
+    w_smooth: float = 0.001
+    w_reproj: float = 0.01
+    upstream: float = 1.0
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class StepHarness:
+    def __init__(self, path: str):
+        self.path = path
+        L = C.CDLL(path)
+        L.cadh_build_info.restype = C.c_char_p
+        vp = C.c_void_p
+        L.cadh_loss_step.argtypes = [C.POINTER(_Cfg), vp, vp, vp, vp, vp, vp, vp, vp, C.c_char_p, C.c_int]
+        L.cadh_components.argtypes = [C.POINTER(_Cfg), vp, vp, vp, vp, vp, vp, C.c_char_p, C.c_int]
+        L.cadh_metrics_eval.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_float, C.c_float, vp, vp,
+                                        C.c_char_p, C.c_int]
+        L.cadh_metrics_train.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_char_p, C.c_int]
+        L.cadh_time_steps.argtypes = [C.POINTER(_Cfg), vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
+                                      C.c_char_p, C.c_int]
+        L.cadh_set_num_threads.argtypes = [C.c_int]
+        self.L = L
+
+    # ------------------------------------------------------------------
+    def info(self) -> str:
+        return self.L.cadh_build_info().decode()
+
+    def is_dropin(self) -> bool:
+        return bool(self.L.cadh_is_dropin())
+
+    def num_threads(self) -> int:
+        return int(self.L.cadh_num_threads())
+
+    def set_num_threads(self, n: int):
+        self.L.cadh_set_num_threads(int(n))
+
+    def cuda_available(self) -> bool:
+        return bool(self.L.cadh_cuda_available())
+
+    def _cfg(self, cfg: StepCfg, pred, K) -> _Cfg:
+        B, _, H, W = pred.shape
+        kb = 1 if (K is not None and K.ndim == 3) else 0
+        return _Cfg(B, H, W, kb, cfg.device, cfg.w_si, cfg.w_grad, cfg.w_smooth, cfg.w_reproj, cfg.term, cfg.upstream)
+
+    @staticmethod
+    def _raise(err):
+        raise RuntimeError(err.value.decode(errors="replace"))
+
+    # ------------------------------------------------------------------
+    def loss_step(self, cfg: StepCfg, pred, gt, rgb=None, K=None, mask=None, want_grad: bool = True):
+        """One training-shaped step.  Returns (loss float, loss rank, loss numel, grad ndarray|None)."""
+        pred, gt, rgb, K = _f32(pred), _f32(gt), _f32(rgb), _f32(K)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        c = self._cfg(cfg, pred, K)
+        loss = C.c_float(0)
+        meta = (C.c_int64 * 2)()
+        grad = np.empty_like(pred) if want_grad else None
+        err = C.create_string_buffer(2048)
+        rc = self.L.cadh_loss_step(C.byref(c), _p(pred), _p(gt), _p(rgb), _p(K), _p(m), C.byref(loss), meta, _p(grad),
+                                   err, len(err))
+        if rc:
+            self._raise(err)
+        return float(loss.value), int(meta[0]), int(meta[1]), grad
+
+    def components(self, cfg: StepCfg, pred, gt, rgb, K, mask=None):
+        pred, gt, rgb, K = _f32(pred), _f32(gt), _f32(rgb), _f32(K)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        c = self._cfg(cfg, pred, K)
+        out = (C.c_float * 4)()
+        err = C.create_string_buffer(2048)
+        rc = self.L.cadh_components(C.byref(c), _p(pred), _p(gt), _p(rgb), _p(K), _p(m), out, err, len(err))
+        if rc:
+            self._raise(err)
+        return {"si_loss": out[0], "grad_loss": out[1], "smooth_loss": out[2], "reproj_loss": out[3]}
+
+    def metrics_eval(self, device: int, pred, gt, mask=None, min_depth=0.1, max_depth=10.0):
+        pred, gt = _f32(pred), _f32(gt)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        B, _, H, W = pred.shape
+        out = (C.c_float * 12)()
+        cnt = (C.c_int64 * 4)()
+        err = C.create_string_buffer(2048)
+        rc = self.L.cadh_metrics_eval(B, H, W, device, _p(pred), _p(gt), _p(m), min_depth, max_depth, out, cnt, err,
+                                      len(err))
+        if rc:
+            self._raise(err)
+        return [float(x) for x in out], [int(x) for x in cnt]
+
+    def metrics_train(self, device: int, pred, gt):
+        pred, gt = _f32(pred), _f32(gt)
+        B, _, H, W = pred.shape
+        out = (C.c_float * 7)()
+        cnt = (C.c_int64 * 4)()
+        err = C.create_string_buffer(2048)
+        rc = self.L.cadh_metrics_train(B, H, W, device, _p(pred), _p(gt), out, cnt, err, len(err))
+        if rc:
+            self._raise(err)
+        return [float(x) for x in out], [int(x) for x in cnt]
+
+    def time_steps(self, cfg: StepCfg, pred, gt, rgb, K, mask=None, with_metrics=False, include_h2d=False,
+                   warmup=1, iters=5):
+        """Per-iteration wall milliseconds of [h2d] forward+backward [+metrics] + loss.item()."""
+        pred, gt, rgb, K = _f32(pred), _f32(gt), _f32(rgb), _f32(K)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        c = self._cfg(cfg, pred, K)
+        ms = (C.c_double * iters)()
+        last = C.c_float(0)
+        err = C.create_string_buffer(2048)
+        rc = self.L.cadh_time_steps(C.byref(c), _p(pred), _p(gt), _p(rgb), _p(K), _p(m), int(with_metrics),
+                                    int(include_h2d), warmup, iters, ms, C.byref(last), err, len(err))
+        if rc:
+            self._raise(err)
+        return [float(x) for x in ms], float(last.value)

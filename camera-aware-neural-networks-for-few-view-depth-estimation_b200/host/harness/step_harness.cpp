@@ -1,0 +1,366 @@
+// Trainer-shaped step harness for the depth-loss hot path.
+//
+// This translation unit is written ONLY against the public class interface of
+//   loss/depth_loss.h          (reference: src/loss/depth_loss.h:20-479)
+//   evaluation/depth_metrics.h (reference: src/evaluation/depth_metrics.h:28-333)
+// and is compiled twice from the same source:
+//   * with  -I <pkg>/host  -DCADL_DROPIN   -> libcadl_host.so  (the B200 drop-in, product path)
+//   * with  -I /root/reference/src         -> oracle/_ref/libcadl_refharness.so (the unmodified
+//                                             reference on LibTorch: parity oracle + CPU baseline)
+// That one source builds against both header sets is the source-compatibility check of the
+// drop-in boundary.
+//
+// The step it performs is the one the reference trainers perform per batch
+// (src/training/production_trainer.h:192-215): stack -> .to(device) -> forwardWithIntrinsics ->
+// backward -> loss.item<float>().  The model is replaced by a leaf tensor `pred` with
+// requires_grad, so pred.grad() is exactly dLoss/dpred.
+//
+// Everything crossing this boundary is plain C (host pointers + sizes); no torch types.
+
+#include <sstream>   // the reference's depth_metrics.h uses these without including them
+#include <iomanip>   // (src/evaluation/depth_metrics.h:309-312,219)
+#include <array>
+#include <torch/torch.h>
+#include <chrono>
+#include <cstring>
+#include <cstdint>
+#include <string>
+
+#include "loss/depth_loss.h"
+#include "evaluation/depth_metrics.h"
+#ifdef CADL_DROPIN
+#include "training/validation_metrics.h"
+#endif
+
+using namespace camera_aware_depth;
+
+extern "C" {
+
+typedef struct {
+    int B, H, W;
+    int k_batched;   // 1: K is (B,3,3); 0: K is (3,3) broadcast (depth_loss.h:278-280)
+    int device;      // -1: CPU, >=0: CUDA ordinal
+    float w_si, w_grad, w_smooth, w_reproj;
+    int term;        // 0 forwardWithIntrinsics, 1 SI, 2 grad-matching, 3 smoothness, 4 reprojection,
+                     // 5 CombinedDepthLoss::forward (no intrinsics)
+    float upstream;  // (loss * upstream).backward(); 1.0f reproduces the trainers
+} cadh_step_cfg;
+
+}  // extern "C"
+
+namespace {
+
+torch::Device pick_device(int device) {
+    return device < 0 ? torch::Device(torch::kCPU) : torch::Device(torch::kCUDA, device);
+}
+
+void sync_device(const torch::Device& dev) {
+    if (dev.is_cuda()) torch::cuda::synchronize(dev.index());
+}
+
+struct Batch {
+    torch::Tensor pred, gt, rgb, K;
+    torch::optional<torch::Tensor> mask;
+};
+
+torch::Tensor host_view(const float* p, at::IntArrayRef shape) {
+    return torch::from_blob(const_cast<float*>(p), shape, torch::kFloat32);
+}
+
+// production_trainer.h:192-194 : host batch -> device
+Batch to_device(const cadh_step_cfg& c, const float* pred, const float* gt, const float* rgb,
+                const float* K, const uint8_t* mask, const torch::Device& dev) {
+    Batch b;
+    b.pred = host_view(pred, {c.B, 1, c.H, c.W}).to(dev).clone();
+    b.gt = host_view(gt, {c.B, 1, c.H, c.W}).to(dev).clone();
+    if (rgb) b.rgb = host_view(rgb, {c.B, 3, c.H, c.W}).to(dev).clone();
+    if (K) {
+        b.K = (c.k_batched ? host_view(K, {c.B, 3, 3}) : host_view(K, {3, 3})).to(dev).clone();
+    }
+    if (mask) {
+        b.mask = torch::from_blob(const_cast<uint8_t*>(mask), {c.B, 1, c.H, c.W}, torch::kBool)
+                     .to(dev).clone();
+    }
+    return b;
+}
+
+torch::Tensor run_term(const cadh_step_cfg& c, CombinedDepthLoss& combined, Batch& b) {
+    switch (c.term) {
+        case 0: return combined.forwardWithIntrinsics(b.pred, b.gt, b.rgb, b.K, b.mask);
+        case 1: { ScaleInvariantLoss l; return l.forward(b.pred, b.gt, b.mask); }
+        case 2: { GradientMatchingLoss l; return l.forward(b.pred, b.gt, b.mask); }
+        case 3: { SmoothnessLoss l; return l.forward(b.pred, b.rgb); }
+        case 4: { ReprojectionLoss l; return l.forward(b.pred, b.gt, b.K, b.mask); }
+        case 5: return combined.forward(b.pred, b.gt, b.rgb, b.mask);
+        default: TORCH_CHECK(false, "cadh: unknown term ", c.term);
+    }
+}
+
+int fail(char* err, int errlen, const std::exception& e) {
+    if (err && errlen > 0) {
+        std::strncpy(err, e.what(), errlen - 1);
+        err[errlen - 1] = 0;
+    }
+    return 1;
+}
+
+#ifndef CADL_DROPIN
+// Integer delta counts with the reference's own ops (depth_metrics.h:154-161,57-66,219-229):
+// the float mean the reference reports cannot hold counts above 2^24 exactly, so parity on
+// counts is defined against (ratio < thr).sum() of the same tensors.
+void ref_ops_eval_counts(torch::Tensor pred, torch::Tensor gt, torch::optional<torch::Tensor> user,
+                         float min_d, float max_d, int64_t counts[4]) {
+    if (pred.dim() == 3) pred = pred.unsqueeze(1);
+    if (gt.dim() == 3) gt = gt.unsqueeze(1);
+    auto mask = (gt > min_d) & (gt < max_d);
+    if (user.has_value()) {
+        auto um = user.value();
+        if (um.dim() == 3) um = um.unsqueeze(1);
+        mask = mask & um.to(torch::kBool);
+    }
+    auto p = pred.masked_select(mask);
+    auto g = gt.masked_select(mask);
+    counts[0] = p.numel();
+    counts[1] = counts[2] = counts[3] = 0;
+    if (counts[0] == 0) return;
+    p = torch::clamp(p, min_d, max_d);
+    auto ratio = torch::max(p / g, g / p);
+    float thr[3] = {1.25f, 1.25f * 1.25f, 1.25f * 1.25f * 1.25f};
+    for (int i = 0; i < 3; ++i) counts[1 + i] = (ratio < thr[i]).sum().item<int64_t>();
+}
+
+// Restatement, op for op, of the trainers' private computeDepthMetrics
+// (src/training/tensorboard_trainer_enhanced.h:400-439; duplicate at tensorboard_trainer.h:348-387).
+// The trainer headers cannot be included here: they pull in OpenCV.
+struct ValidationMetrics {
+    float loss = 0.0f, abs_rel = 0.0f, sq_rel = 0.0f, rmse = 0.0f, rmse_log = 0.0f;
+    float a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+};
+ValidationMetrics computeDepthMetrics(const torch::Tensor& pred, const torch::Tensor& gt) {
+    ValidationMetrics metrics;
+    auto pred_flat = pred.view({-1});
+    auto gt_flat = gt.view({-1});
+    auto valid_mask = gt_flat > 0.0f;
+    auto pred_valid = pred_flat.masked_select(valid_mask);
+    auto gt_valid = gt_flat.masked_select(valid_mask);
+    if (pred_valid.numel() == 0) return metrics;
+    auto abs_diff = torch::abs(pred_valid - gt_valid);
+    metrics.abs_rel = (abs_diff / gt_valid).mean().item<float>();
+    metrics.sq_rel = ((abs_diff * abs_diff) / gt_valid).mean().item<float>();
+    metrics.rmse = torch::sqrt((abs_diff * abs_diff).mean()).item<float>();
+    auto log_diff = torch::abs(torch::log(pred_valid + 1e-8) - torch::log(gt_valid + 1e-8));
+    metrics.rmse_log = torch::sqrt((log_diff * log_diff).mean()).item<float>();
+    auto ratio = torch::max(pred_valid / gt_valid, gt_valid / pred_valid);
+    metrics.a1 = (ratio < 1.25f).to(torch::kFloat32).mean().item<float>();
+    metrics.a2 = (ratio < 1.5625f).to(torch::kFloat32).mean().item<float>();
+    metrics.a3 = (ratio < 1.953125f).to(torch::kFloat32).mean().item<float>();
+    return metrics;
+}
+
+void ref_ops_train_counts(const torch::Tensor& pred, const torch::Tensor& gt, int64_t counts[4]) {
+    auto pf = pred.reshape({-1});
+    auto gf = gt.reshape({-1});
+    auto m = gf > 0.0f;
+    auto p = pf.masked_select(m);
+    auto g = gf.masked_select(m);
+    counts[0] = p.numel();
+    counts[1] = counts[2] = counts[3] = 0;
+    if (counts[0] == 0) return;
+    auto ratio = torch::max(p / g, g / p);
+    counts[1] = (ratio < 1.25f).sum().item<int64_t>();
+    counts[2] = (ratio < 1.5625f).sum().item<int64_t>();
+    counts[3] = (ratio < 1.953125f).sum().item<int64_t>();
+}
+#endif  // !CADL_DROPIN
+
+const char* kEvalKeys[12] = {"abs_rel", "sq_rel", "rmse", "rmse_log", "mae", "log10",
+                             "delta_1.25", "delta_1.25^2", "delta_1.25^3",
+                             "num_valid_pixels", "mean_pred_depth", "mean_gt_depth"};
+
+}  // namespace
+
+extern "C" {
+
+const char* cadh_build_info() {
+#ifdef CADL_DROPIN
+    return "cadl drop-in headers (sm_100a CUDA kernels behind the reference class API)";
+#else
+    return "unmodified reference headers on LibTorch";
+#endif
+}
+
+int cadh_is_dropin() {
+#ifdef CADL_DROPIN
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+int cadh_num_threads() { return torch::get_num_threads(); }
+void cadh_set_num_threads(int n) { torch::set_num_threads(n); }
+int cadh_cuda_available() { return torch::cuda::is_available() ? 1 : 0; }
+
+// One training-shaped step: H2D, forward, backward, D2H of the loss (and of pred.grad if asked).
+// out_loss_meta[0] = loss.dim(), [1] = loss.numel()  (ranks are part of the contract: SURVEY 8b).
+int cadh_loss_step(const cadh_step_cfg* cfg, const float* pred, const float* gt, const float* rgb,
+                   const float* K, const uint8_t* mask, float* out_loss, int64_t* out_loss_meta,
+                   float* out_grad, char* err, int errlen) {
+    try {
+        const cadh_step_cfg& c = *cfg;
+        auto dev = pick_device(c.device);
+        Batch b = to_device(c, pred, gt, rgb, K, mask, dev);
+        b.pred.set_requires_grad(true);
+        CombinedDepthLoss combined(c.w_si, c.w_grad, c.w_smooth, c.w_reproj);
+        auto loss = run_term(c, combined, b);
+        if (out_loss_meta) {
+            out_loss_meta[0] = loss.dim();
+            out_loss_meta[1] = loss.numel();
+        }
+        if (out_grad) {
+            if (loss.requires_grad()) {
+                auto scaled = (c.upstream == 1.0f) ? loss : loss * c.upstream;
+                scaled.sum().backward();
+            }
+            auto g = b.pred.grad();
+            if (!g.defined()) g = torch::zeros_like(b.pred);
+            auto gh = g.to(torch::kCPU).contiguous();
+            std::memcpy(out_grad, gh.data_ptr<float>(), sizeof(float) * gh.numel());
+        }
+        *out_loss = loss.sum().item<float>();
+        return 0;
+    } catch (const std::exception& e) {
+        return fail(err, errlen, e);
+    }
+}
+
+// CombinedDepthLoss::getComponentsWithIntrinsics (depth_loss.h:454-467) -> si, grad, smooth, reproj
+int cadh_components(const cadh_step_cfg* cfg, const float* pred, const float* gt, const float* rgb,
+                    const float* K, const uint8_t* mask, float out4[4], char* err, int errlen) {
+    try {
+        const cadh_step_cfg& c = *cfg;
+        auto dev = pick_device(c.device);
+        Batch b = to_device(c, pred, gt, rgb, K, mask, dev);
+        torch::NoGradGuard ng;
+        CombinedDepthLoss combined(c.w_si, c.w_grad, c.w_smooth, c.w_reproj);
+        auto m = combined.getComponentsWithIntrinsics(b.pred, b.gt, b.rgb, b.K, b.mask);
+        out4[0] = m.at("si_loss");
+        out4[1] = m.at("grad_loss");
+        out4[2] = m.at("smooth_loss");
+        out4[3] = m.at("reproj_loss");
+        return 0;
+    } catch (const std::exception& e) {
+        return fail(err, errlen, e);
+    }
+}
+
+// DepthMetrics::compute (depth_metrics.h:40-88): 12 floats in kEvalKeys order + integer counts
+// {n_valid, n(delta<1.25), n(<1.25^2), n(<1.25^3)}.
+int cadh_metrics_eval(int B, int H, int W, int device, const float* pred, const float* gt,
+                      const uint8_t* mask, float min_d, float max_d, float out12[12],
+                      int64_t counts[4], char* err, int errlen) {
+    try {
+        cadh_step_cfg c{};
+        c.B = B; c.H = H; c.W = W; c.device = device;
+        auto dev = pick_device(device);
+        Batch b = to_device(c, pred, gt, nullptr, nullptr, mask, dev);
+        torch::NoGradGuard ng;
+        auto m = DepthMetrics::compute(b.pred, b.gt, b.mask, min_d, max_d);
+        for (int i = 0; i < 12; ++i) out12[i] = m.at(kEvalKeys[i]);
+        if (counts) {
+#ifdef CADL_DROPIN
+            DepthMetrics::computeCounts(b.pred, b.gt, b.mask, min_d, max_d, counts);
+#else
+            ref_ops_eval_counts(b.pred, b.gt, b.mask, min_d, max_d, counts);
+#endif
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        return fail(err, errlen, e);
+    }
+}
+
+// The trainers' computeDepthMetrics (tensorboard_trainer_enhanced.h:400-439) on one (1,H,W) sample
+// or any flat set of N = B*H*W values: out7 = abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3.
+int cadh_metrics_train(int B, int H, int W, int device, const float* pred, const float* gt,
+                       float out7[7], int64_t counts[4], char* err, int errlen) {
+    try {
+        cadh_step_cfg c{};
+        c.B = B; c.H = H; c.W = W; c.device = device;
+        auto dev = pick_device(device);
+        Batch b = to_device(c, pred, gt, nullptr, nullptr, nullptr, dev);
+        torch::NoGradGuard ng;
+        auto m = computeDepthMetrics(b.pred, b.gt);
+        out7[0] = m.abs_rel; out7[1] = m.sq_rel; out7[2] = m.rmse; out7[3] = m.rmse_log;
+        out7[4] = m.a1; out7[5] = m.a2; out7[6] = m.a3;
+        if (counts) {
+#ifdef CADL_DROPIN
+            computeDepthMetricsCounts(b.pred, b.gt, counts);
+#else
+            ref_ops_train_counts(b.pred, b.gt, counts);
+#endif
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        return fail(err, errlen, e);
+    }
+}
+
+// Timing loop over the same step:  per iteration
+//   [h2d of rgb/gt/K/pred if include_h2d] zero grad -> forward -> backward [-> metrics] -> loss.item
+// out_ms[i] = wall milliseconds of iteration i (device synchronised on both sides).
+int cadh_time_steps(const cadh_step_cfg* cfg, const float* pred, const float* gt, const float* rgb,
+                    const float* K, const uint8_t* mask, int with_metrics, int include_h2d,
+                    int warmup, int iters, double* out_ms, float* out_last_loss, char* err,
+                    int errlen) {
+    try {
+        const cadh_step_cfg& c = *cfg;
+        auto dev = pick_device(c.device);
+        Batch b = to_device(c, pred, gt, rgb, K, mask, dev);
+        // pinned staging copies for the h2d variant
+        Batch h;
+        if (include_h2d) {
+            auto pin = [&](const torch::Tensor& t) {
+                auto cpu = t.to(torch::kCPU).contiguous();
+                return dev.is_cuda() ? cpu.pin_memory() : cpu;
+            };
+            h.pred = pin(b.pred); h.gt = pin(b.gt);
+            if (b.rgb.defined()) h.rgb = pin(b.rgb);
+            if (b.K.defined()) h.K = pin(b.K);
+        }
+        CombinedDepthLoss combined(c.w_si, c.w_grad, c.w_smooth, c.w_reproj);
+        float last = 0.f;
+        for (int it = 0; it < warmup + iters; ++it) {
+            sync_device(dev);
+            auto t0 = std::chrono::steady_clock::now();
+            if (include_h2d) {
+                b.pred = h.pred.to(dev, /*non_blocking=*/true);
+                b.gt = h.gt.to(dev, true);
+                if (h.rgb.defined()) b.rgb = h.rgb.to(dev, true);
+                if (h.K.defined()) b.K = h.K.to(dev, true);
+            }
+            b.pred = b.pred.detach();
+            b.pred.set_requires_grad(true);       // optimizer_->zero_grad() equivalent: fresh leaf
+            auto loss = run_term(c, combined, b);
+            if (loss.requires_grad()) loss.sum().backward();
+            if (with_metrics) {
+                torch::NoGradGuard ng;
+                auto pd = b.pred.detach();
+                auto m1 = DepthMetrics::compute(pd, b.gt);
+                auto m2 = computeDepthMetrics(pd, b.gt);
+                last += 0.f * (m1.at("abs_rel") + m2.abs_rel);
+            }
+            last = loss.sum().item<float>();
+            sync_device(dev);
+            auto t1 = std::chrono::steady_clock::now();
+            if (it >= warmup)
+                out_ms[it - warmup] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        }
+        if (out_last_loss) *out_last_loss = last;
+        return 0;
+    } catch (const std::exception& e) {
+        return fail(err, errlen, e);
+    }
+}
+
+}  // extern "C"

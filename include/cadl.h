@@ -1,0 +1,179 @@
+/* cadl -- camera-aware depth-loss kernels for NVIDIA B200 (sm_100a): the C ABI.
+ *
+ * This is the drop-in boundary of the hot path.  The reference has no FFI for this path: its
+ * loss/metric classes are header-only LibTorch op chains (src/loss/depth_loss.h,
+ * src/evaluation/depth_metrics.h).  The replacement headers under <pkg>/host/ keep those class
+ * signatures and call ONLY the functions declared here; each entry point names the reference
+ * interface it replaces (file:line relative to the reference root).
+ *
+ * Conventions
+ *   - plain pointers and sizes; no torch types.  All data pointers are DEVICE pointers on the
+ *     current CUDA device unless marked "host".  fp32, NCHW contiguous:
+ *       pred (B,1,H,W)  gt (B,1,H,W)  rgb (B,3,H,W)  K (B,3,3) or (3,3) row-major
+ *       mask (B,1,H,W) bytes (torch::kBool storage), may be NULL
+ *   - the caller owns every buffer (results, gradient, workspace); kernels never allocate.
+ *   - every call is asynchronous on `stream` (a cudaStream_t) and re-entrant; two calls may run
+ *     concurrently iff they use different workspaces.
+ *   - return value: 0 = ok, CADL_ERR_* (<1000) = argument error detected before launch,
+ *     1000 + cudaError_t = launch/runtime error.  Nothing throws.  cadl_error_string() names it.
+ *   - there is NO CPU fallback: without a CUDA device the calls return 1000+cudaErrorNoDevice.
+ */
+#ifndef CADL_H_
+#define CADL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CADL_VERSION 100
+
+typedef void* cadl_stream_t; /* cudaStream_t */
+
+/* loss terms (bitmask) */
+#define CADL_TERM_SI 1u      /* ScaleInvariantLoss      depth_loss.h:20-69   */
+#define CADL_TERM_GRAD 2u    /* GradientMatchingLoss    depth_loss.h:82-167  */
+#define CADL_TERM_SMOOTH 4u  /* SmoothnessLoss          depth_loss.h:178-238 */
+#define CADL_TERM_REPROJ 8u  /* ReprojectionLoss        depth_loss.h:255-355 */
+#define CADL_TERM_ALL 15u
+
+/* metric variants (bitmask) */
+#define CADL_METRICS_EVAL 1u  /* DepthMetrics::compute            depth_metrics.h:40-88 */
+#define CADL_METRICS_TRAIN 2u /* trainers' computeDepthMetrics    tensorboard_trainer_enhanced.h:400-439 */
+
+#define CADL_MAX_SCALES 4
+
+enum {
+    CADL_OK = 0,
+    CADL_ERR_NULL = 1,        /* a required pointer is NULL */
+    CADL_ERR_SHAPE = 2,       /* B,H,W out of range for the requested terms */
+    CADL_ERR_WORKSPACE = 3,   /* workspace too small or misaligned */
+    CADL_ERR_UNSUPPORTED = 4, /* term combination / num_scales not provided by this build */
+    CADL_ERR_ALIGN = 5,       /* a data pointer is not 4-byte aligned */
+    CADL_ERR_CUDA = 1000      /* 1000 + cudaError_t */
+};
+
+/* The constructor arguments of the reference classes, as one POD. */
+typedef struct cadl_params {
+    uint32_t terms;   /* CADL_TERM_* to evaluate */
+    uint32_t metrics; /* CADL_METRICS_* to evaluate in the same pass over pred/gt (0 = none) */
+    float w_si, w_grad, w_smooth, w_reproj; /* CombinedDepthLoss ctor, depth_loss.h:368-371 */
+    float si_lambda;                        /* ScaleInvariantLoss ctor, depth_loss.h:22 (0.5) */
+    float eps_si, eps_grad, eps_smooth, eps_reproj; /* depth_loss.h:22,84,180,257 (1e-6 each) */
+    int32_t num_scales;                     /* GradientMatchingLoss ctor, depth_loss.h:84 (4) */
+    int32_t k_batched;                      /* 1: K is (B,3,3); 0: (3,3) broadcast, depth_loss.h:278-280 */
+    float min_depth, max_depth;             /* DepthMetrics::compute, depth_metrics.h:44-45 (0.1, 10) */
+    float upstream;                         /* dL/dloss folded into the gradient (1.0 = loss.backward()) */
+    /* exact-global-batch mode (SURVEY 8e mode B): this rank holds B of global_B images */
+    int32_t global_B;                       /* 0 or B: single process */
+} cadl_params;
+
+/* Everything the hot path returns, written on the device by the last block of the last kernel.
+ * float members are what the reference returns as fp32 tensors / .item<float>(); the fp64 and
+ * integer members are the exact accumulators they were rounded from. */
+typedef struct cadl_results {
+    /* losses (un-weighted terms, and the weighted total of the requested terms) */
+    float loss_total, loss_si, loss_grad, loss_smooth, loss_reproj;
+    float _pad0[3];
+    double d_total, d_si, d_grad, d_smooth, d_reproj;
+    int64_t n_si, n_reproj; /* valid-pixel counts (depth_loss.h:52, :323-325) */
+    /* DepthMetrics::compute: abs_rel sq_rel rmse rmse_log mae log10 d1 d2 d3 n_valid mean_pred mean_gt */
+    float eval[12];
+    int64_t eval_counts[4]; /* n_valid, #(ratio<1.25), #(<1.25^2), #(<1.25^3) */
+    /* computeDepthMetrics: abs_rel sq_rel rmse rmse_log a1 a2 a3 (+ pad) */
+    float train[8];
+    int64_t train_counts[4];
+} cadl_results;
+
+void cadl_default_params(cadl_params* p);
+int cadl_version(void);
+/* sizeof(cadl_params) / sizeof(cadl_results) of this build: lets an FFI binding verify its mirror */
+size_t cadl_sizeof_params(void);
+size_t cadl_sizeof_results(void);
+const char* cadl_error_string(int code);
+
+/* Bytes of workspace for a (B,H,W) problem; 256-byte aligned pointer required.  The workspace must
+ * be zeroed ONCE (cadl_workspace_init) and is left clean by every call. */
+size_t cadl_workspace_bytes(int B, int H, int W);
+int cadl_workspace_init(void* workspace, size_t bytes, cadl_stream_t stream);
+
+/* Fused forward+backward of the requested loss terms (+ optional metrics):
+ *   replaces CombinedDepthLoss::forwardWithIntrinsics + autograd backward
+ *   (depth_loss.h:416-433; call site src/training/production_trainer.h:203-206), and, with
+ *   terms = SI|GRAD|SMOOTH, CombinedDepthLoss::forward (depth_loss.h:390-404).
+ * grad_pred (B,1,H,W) receives upstream * dL_total/dpred; may be NULL (forward only, e.g.
+ * getComponents*, depth_loss.h:438-467).  rgb may be NULL without TERM_SMOOTH, K without
+ * TERM_REPROJ. */
+int cadl_stack_fwd_bwd(const float* pred, const float* gt, const float* rgb, const float* K,
+                       const uint8_t* mask, int B, int H, int W, const cadl_params* params,
+                       float* grad_pred, cadl_results* results, void* workspace,
+                       size_t workspace_bytes, cadl_stream_t stream);
+
+/* The same computation split at its one global dependency: phase A reduces the
+ * batch-global scalars into a vector of `cadl_stats_count()` doubles at
+ * (char*)workspace + cadl_stats_offset(); a multi-GPU caller all-reduces (sum) that vector between
+ * the two calls and sets params->global_B; phase B writes gradients and results. */
+int cadl_stack_reduce(const float* pred, const float* gt, const uint8_t* mask, int B, int H, int W,
+                      const cadl_params* params, void* workspace, size_t workspace_bytes,
+                      cadl_stream_t stream);
+int cadl_stack_grad(const float* pred, const float* gt, const float* rgb, const float* K,
+                    const uint8_t* mask, int B, int H, int W, const cadl_params* params,
+                    float* grad_pred, cadl_results* results, void* workspace,
+                    size_t workspace_bytes, cadl_stream_t stream);
+size_t cadl_stats_offset(void);
+int cadl_stats_count(void);
+
+/* Single-term entry points (each = the class's forward + its autograd backward). */
+/* ScaleInvariantLoss::forward, depth_loss.h:33-64 */
+int cadl_si_fwd_bwd(const float* pred, const float* gt, const uint8_t* mask, int B, int H, int W,
+                    float lambda, float eps, float upstream, float* grad_pred,
+                    cadl_results* results, void* workspace, size_t workspace_bytes,
+                    cadl_stream_t stream);
+/* GradientMatchingLoss::forward, depth_loss.h:95-166 */
+int cadl_gradmatch_fwd_bwd(const float* pred, const float* gt, int B, int H, int W, int num_scales,
+                           float eps, float upstream, float* grad_pred, cadl_results* results,
+                           void* workspace, size_t workspace_bytes, cadl_stream_t stream);
+/* SmoothnessLoss::forward, depth_loss.h:189-234 */
+int cadl_smooth_fwd_bwd(const float* pred, const float* rgb, int B, int H, int W, float eps,
+                        float upstream, float* grad_pred, cadl_results* results, void* workspace,
+                        size_t workspace_bytes, cadl_stream_t stream);
+/* ReprojectionLoss::forward, depth_loss.h:268-331 */
+int cadl_reproj_fwd_bwd(const float* pred, const float* gt, const float* K, int k_batched,
+                        const uint8_t* mask, int B, int H, int W, float eps, float upstream,
+                        float* grad_pred, cadl_results* results, void* workspace,
+                        size_t workspace_bytes, cadl_stream_t stream);
+
+/* autograd backward of the shim: grad_out[i] = grad_in[i] * (*upstream_dev).  A device scalar so no
+ * host sync is needed; when *upstream_dev == 1.0f and grad_out == grad_in no memory is touched. */
+int cadl_scale_grad(const float* grad_in, const float* upstream_dev, float* grad_out, size_t n,
+                    cadl_stream_t stream);
+
+/* Metrics only (no loss): DepthMetrics::compute (depth_metrics.h:40-88) and/or the trainers'
+ * computeDepthMetrics (tensorboard_trainer_enhanced.h:400-439) over n = B*H*W values. */
+int cadl_metrics(const float* pred, const float* gt, const uint8_t* mask, size_t n,
+                 uint32_t which, float min_depth, float max_depth, cadl_results* results,
+                 void* workspace, size_t workspace_bytes, cadl_stream_t stream);
+
+/* RayDirectionComputer (src/preprocessing/ray_direction_computer.cpp):
+ *   layout 0: out (B, H*W, 3) row-major -- computeRayDirections, :17-62
+ *   layout 1: out (B, 3, H, W) planar   -- computeRayDirectionsMaps, :64-101 (the loader's layout,
+ *             src/data/sunrgbd_loader.cpp:345-347)
+ *   pose (B,4,4) row-major or NULL: rotate by R and re-normalise -- transformRaysToWorld, :103-127 */
+int cadl_rays_from_K(const float* K, int k_batched, const float* pose, int B, int H, int W,
+                     int layout, float* out, cadl_stream_t stream);
+
+/* Builder extension (NOT in the reference, whose forwardPhotometric is a stub returning zeros,
+ * depth_loss.h:343-351): photometric reprojection  back-project -> [R|t] -> project -> bilinear
+ * sample -> L1 residual, with explicit backward to depth.  T (B,4,4) row-major target->source.
+ * results->loss_reproj receives the loss; parity is defined against oracle/oracle_torch.py only. */
+int cadl_photometric_fwd_bwd(const float* pred, const float* K, int k_batched, const float* T,
+                             const float* source, const float* target, int B, int H, int W,
+                             float eps, float upstream, float* grad_pred, cadl_results* results,
+                             void* workspace, size_t workspace_bytes, cadl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CADL_H_ */

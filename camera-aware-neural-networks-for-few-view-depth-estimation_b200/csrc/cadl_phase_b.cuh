@@ -110,8 +110,10 @@ __device__ __forceinline__ void scale_dims(const PhaseBArgs& a, int s, int& Hs, 
     Ws = a.W >> s;
     double nx = (double)a.global_B * Hs * (Ws - 1);
     double ny = (double)a.global_B * (Hs - 1) * Ws;
-    inv_nx = (float)(1.0 / nx);
-    inv_ny = (float)(1.0 / ny);
+    // no edges at all (Ws == 1 / Hs == 1): the reference's mean over an empty tensor is NaN for the LOSS
+    // (finalize_results keeps that: 0/0) but contributes no gradient
+    inv_nx = nx > 0.0 ? (float)(1.0 / nx) : 0.f;
+    inv_ny = ny > 0.0 ? (float)(1.0 / ny) : 0.f;
 }
 
 // Final reduction + results, executed by the last CTA of phase B (all threads of the block).
@@ -264,10 +266,17 @@ __device__ __forceinline__ bool publish_partials(const PhaseBArgs& a, float (&ac
     return *s_last != 0;
 }
 
-// Pointwise terms for one pixel; returns the (weighted, upstream-scaled) gradient contribution.
+// Per-pixel camera geometry of the reprojection term (depth_loss.h:283-300).
+struct RpGeom {
+    float ax, ay;     // (u - cx), (v - cy)
+    float fxe, fye;   // fx + eps, fy + eps
+    float xh, yh;     // ax / fxe, ay / fye  (d pX / d p)
+};
+
+// Pointwise terms for one pixel; returns the weighted gradient contribution (upstream applied by caller).
 template <int F>
 __device__ __forceinline__ float pointwise_px(const PhaseBArgs& a, const Derived& dv, float p, float g,
-                                              bool has_mask, bool um, float d_si, float r2,
+                                              bool has_mask, bool um, float d_si, const RpGeom& q,
                                               float& rp_e_acc) {
     float gr = 0.f;
     if constexpr (F & FB_SI) {
@@ -278,10 +287,19 @@ __device__ __forceinline__ float pointwise_px(const PhaseBArgs& a, const Derived
     if constexpr (F & FB_RP) {
         bool m = has_mask ? um : (g > a.eps_rp);
         if (m && dv.rp_on) {
-            float dz = p - g;
-            float e = sqrtf(dz * dz * r2 + a.eps_rp);            // depth_loss.h:313-315 (factored)
+            // The reference subtracts two back-projected points, X_p - X_g with X = (u-cx)*d/(fx+eps)
+            // (depth_loss.h:299-311).  Where pred ~ gt that difference is dominated by the rounding of
+            // the two quotients, and e ~ sqrt(eps) amplifies it into the gradient (1e-4 of max|g|), so
+            // the same operations are done in the same order; the factored form x_hat*(p-g) would be
+            // more accurate but would not reproduce the reference's values.
+            const float dX = __fdiv_rn(__fmul_rn(q.ax, p), q.fxe) - __fdiv_rn(__fmul_rn(q.ax, g), q.fxe);
+            const float dY = __fdiv_rn(__fmul_rn(q.ay, p), q.fye) - __fdiv_rn(__fmul_rn(q.ay, g), q.fye);
+            const float dZ = p - g;
+            const float ss = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(dX, dX), __fmul_rn(dY, dY)), __fmul_rn(dZ, dZ)), a.eps_rp);
+            const float e = sqrtf(ss);                                                // :313-315
             rp_e_acc += e;
-            gr += a.w_rp * ((dz * r2 / e) * dv.rp_inv_n);
+            // autograd: dL/dp = (dX * xh + dY * yh + dZ) / (e * n)
+            gr += a.w_rp * (((dX * q.xh + dY * q.yh + dZ) / e) * dv.rp_inv_n);
         }
     }
     return gr;
@@ -343,28 +361,31 @@ __global__ void __launch_bounds__(kThreadsB) phase_b_point_kernel(const PhaseBAr
                 um[k] = in ? (has_mask ? (__ldg(a.mask + off + k) != 0) : true) : false;
             }
         }
-        float r2y = 0.f, fx = 1.f, cx = 0.f;
+        RpGeom q{};
+        float cx = 0.f;
         if constexpr (F & FB_RP) {
-            float fy, cy;
+            float fx, fy, cy;
             load_K(a, b, fx, fy, cx, cy);
-            float yh = ((float)y - cy) / (fy + a.eps_rp);       // depth_loss.h:300
-            r2y = yh * yh + 1.0f;
+            q.fxe = fx + a.eps_rp;                               // depth_loss.h:299-300
+            q.fye = fy + a.eps_rp;
+            q.ay = (float)y - cy;
+            q.yh = q.ay / q.fye;
         }
         float out[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            float d_si = 0.f, r2 = 0.f;
+            float d_si = 0.f;
             if constexpr (F & FB_SI) {
                 d_si = logf(clampf(p[k], a.eps_si, 1000.0f)) - logf(clampf(g[k], a.eps_si, 1000.0f));
             }
             if constexpr (F & FB_RP) {
-                float xh = ((float)(x + k) - cx) / (fx + a.eps_rp);   // depth_loss.h:299
-                r2 = xh * xh + r2y;
+                q.ax = (float)(x + k) - cx;
+                q.xh = q.ax / q.fxe;
             }
             bool in = x + k < a.W;
             bool mk = has_mask ? um[k] : in;
             float gr = 0.f;
-            if (in) gr = pointwise_px<F>(a, dv, p[k], g[k], has_mask, mk, d_si, r2, acc[BF_RP_E]);
+            if (in) gr = pointwise_px<F>(a, dv, p[k], g[k], has_mask, mk, d_si, q, acc[BF_RP_E]);
             out[k] = gr * a.upstream;
         }
         if (a.grad) {
@@ -553,13 +574,13 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_tile_kernel(const PhaseB
         const int xl = 4 * lane;                     // local column of this lane's float4
         const int gx0 = x0 + xl;
         float fx = 1.f, fy = 1.f, cx = 0.f, cy = 0.f;
-        float xh2[4] = {0.f, 0.f, 0.f, 0.f};
+        float axk[4] = {0.f, 0.f, 0.f, 0.f}, xhk[4] = {0.f, 0.f, 0.f, 0.f};
         if constexpr (F & FB_RP) {
             load_K(a, b, fx, fy, cx, cy);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                float xh = ((float)(gx0 + k) - cx) / (fx + a.eps_rp);
-                xh2[k] = xh * xh;
+                axk[k] = (float)(gx0 + k) - cx;                 // depth_loss.h:299
+                xhk[k] = axk[k] / (fx + a.eps_rp);
             }
         }
         float inv_nx0 = 0.f, inv_ny0 = 0.f;
@@ -568,8 +589,8 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_tile_kernel(const PhaseB
         if constexpr (SMOOTH) {
             const double HWd = (double)H * W;
             ab = 1.0f / ((float)(a.img_psum[b] / HWd) + a.eps_smooth);      // depth_loss.h:192-193
-            sm_nx = (float)(1.0 / ((double)a.global_B * H * (W - 1)));
-            sm_ny = (float)(1.0 / ((double)a.global_B * (H - 1) * W));
+            sm_nx = W > 1 ? (float)(1.0 / ((double)a.global_B * H * (W - 1))) : 0.f;
+            sm_ny = H > 1 ? (float)(1.0 / ((double)a.global_B * (H - 1) * W)) : 0.f;
         }
         const float inv_ns = 1.0f / (float)a.num_scales;
 
@@ -735,10 +756,12 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_tile_kernel(const PhaseB
             }
 
             if constexpr ((F & (FB_SI | FB_RP)) != 0) {
-                float r2y = 0.f;
+                RpGeom q{};
                 if constexpr (F & FB_RP) {
-                    float yh = ((float)gy - cy) / (fy + a.eps_rp);
-                    r2y = yh * yh + 1.0f;
+                    q.fxe = fx + a.eps_rp;
+                    q.fye = fy + a.eps_rp;
+                    q.ay = (float)gy - cy;                      // depth_loss.h:300
+                    q.yh = q.ay / q.fye;
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -748,8 +771,9 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_tile_kernel(const PhaseB
                         if (GRAD && a.eps_si == a.eps_grad) d_si = lp[k] - lg[k];
                         else d_si = logf(clampf(p[k], a.eps_si, 1000.0f)) - logf(clampf(g[k], a.eps_si, 1000.0f));
                     }
-                    out[k] += pointwise_px<F>(a, dv, p[k], g[k], has_mask, um[k] != 0, d_si, xh2[k] + r2y,
-                                              acc[BF_RP_E]);
+                    q.ax = axk[k];
+                    q.xh = xhk[k];
+                    out[k] += pointwise_px<F>(a, dv, p[k], g[k], has_mask, um[k] != 0, d_si, q, acc[BF_RP_E]);
                 }
             }
 

@@ -131,8 +131,10 @@ struct FusedLossFunction : public torch::autograd::Function<FusedLossFunction> {
                                  int64_t W, std::string params_blob, int64_t result_offset, bool want_grad) {
         cadl_params p;
         std::memcpy(&p, params_blob.data(), sizeof(p));
+        // absent inputs arrive as 0-element placeholders (Function::apply rejects undefined tensors)
+        auto opt = [](const torch::Tensor& t) { return t.numel() == 0 ? torch::Tensor() : t; };
         StackInputs in;
-        in.pred = pred; in.gt = gt; in.rgb = rgb; in.K = K; in.mask = mask;
+        in.pred = pred; in.gt = opt(gt); in.rgb = opt(rgb); in.K = opt(K); in.mask = opt(mask);
         in.B = (int)B; in.H = (int)H; in.W = (int)W;
         torch::Tensor grad;
         if (want_grad) grad = torch::empty_like(pred);
@@ -184,7 +186,10 @@ inline torch::Tensor apply_fused(torch::Tensor pred, torch::Tensor gt, torch::Te
     const int64_t B = pred.size(0), H = pred.size(2), W = pred.size(3);
     std::string blob(reinterpret_cast<const char*>(&p), sizeof(p));
     const bool want_grad = pred.requires_grad() && torch::GradMode::is_enabled();
-    return FusedLossFunction::apply(pred, gt, rgb, K, mask, B, H, W, blob, (int64_t)result_offset, want_grad);
+    auto none_f = torch::empty({0}, pred.options());
+    auto ph = [&](const torch::Tensor& t) { return t.defined() ? t : none_f; };
+    return FusedLossFunction::apply(pred, ph(gt), ph(rgb), ph(K), ph(mask), B, H, W, blob, (int64_t)result_offset,
+                                    want_grad);
 }
 
 }  // namespace cadl_detail

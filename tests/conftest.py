@@ -59,7 +59,7 @@ def load_golden(name):
 
 def rel_err(a, b):
     a, b = float(a), float(b)
-    if a == b:
+    if a == b or (np.isnan(a) and np.isnan(b)):
         return 0.0
     return abs(a - b) / max(abs(b), 1e-30)
 

@@ -58,7 +58,8 @@ class CadlResults(C.Structure):
 
 # every symbol include/cadl.h declares (tests/test_abi.py checks the .so exports each one)
 ABI_SYMBOLS = (
-    "cadl_default_params", "cadl_version", "cadl_sizeof_params", "cadl_sizeof_results", "cadl_error_string", "cadl_workspace_bytes", "cadl_workspace_init",
+    "cadl_default_params", "cadl_version", "cadl_sizeof_params", "cadl_sizeof_results", "cadl_error_string",
+    "cadl_debug_force_generic", "cadl_selftest", "cadl_workspace_bytes", "cadl_workspace_init",
     "cadl_stack_fwd_bwd", "cadl_stack_reduce", "cadl_stack_grad", "cadl_stats_offset", "cadl_stats_count",
     "cadl_si_fwd_bwd", "cadl_gradmatch_fwd_bwd", "cadl_smooth_fwd_bwd", "cadl_reproj_fwd_bwd",
     "cadl_scale_grad", "cadl_metrics", "cadl_rays_from_K", "cadl_photometric_fwd_bwd",
@@ -109,6 +110,9 @@ def lib() -> C.CDLL:
     L.cadl_rays_from_K.argtypes = [f32p, C.c_int, f32p, C.c_int, C.c_int, C.c_int, C.c_int, f32p, vp]
     L.cadl_photometric_fwd_bwd.argtypes = [f32p, f32p, C.c_int, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int,
                                            C.c_float, C.c_float, f32p, vp, vp, C.c_size_t, vp]
+    L.cadl_debug_force_generic.argtypes = [C.c_int]
+    L.cadl_debug_force_generic.restype = None
+    L.cadl_selftest.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_float, vp, vp]
     for name in ABI_SYMBOLS:
         getattr(L, name)   # AttributeError here = the .so does not export what include/cadl.h declares
     if L.cadl_sizeof_params() != C.sizeof(CadlParams) or L.cadl_sizeof_results() != C.sizeof(CadlResults):
@@ -235,6 +239,21 @@ def metrics(pred, gt, mask=None, which: int = METRICS_EVAL | METRICS_TRAIN, min_
                                 _ptr(ws.buf), ws.bytes, _stream(pred))
     _check(rc, "cadl_metrics")
     return ws
+
+
+def force_generic(on: bool):
+    """Test hook: route phase B through the generic kernel even for aligned shapes."""
+    lib().cadl_debug_force_generic(1 if on else 0)
+
+
+def selftest(which: int, lo_bits: int, hi_bits: int, param: float = 0.0, device="cuda:0") -> int:
+    """Number of inputs in [lo_bits, hi_bits] where a device-math replica differs from the CUDA library form."""
+    out = torch.zeros(1, dtype=torch.int64, device=device)
+    with torch.cuda.device(out.device):
+        rc = lib().cadl_selftest(which, lo_bits, hi_bits, param, _ptr(out),
+                                 C.c_void_p(torch.cuda.current_stream(out.device).cuda_stream))
+    _check(rc, "cadl_selftest")
+    return int(out.item())
 
 
 def scale_grad(grad_in, upstream_dev, grad_out):

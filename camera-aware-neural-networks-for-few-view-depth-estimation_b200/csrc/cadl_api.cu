@@ -8,10 +8,39 @@
 #include "cadl_common.cuh"
 #include "cadl_phase_a.cuh"
 #include "cadl_phase_b.cuh"
+#include "cadl_phase_b_fast.cuh"
 #include "cadl_rays.cuh"
 #include "cadl_photometric.cuh"
 
 using namespace cadl;
+
+namespace cadl {
+// Self-test kernels (tests/test_math_gpu.py): the replicas in cadl_math.cuh against the CUDA library forms.
+__global__ void selftest_log_kernel(unsigned lo, unsigned hi, unsigned long long* mism) {
+    unsigned long long bad = 0;
+    for (unsigned long long u = (unsigned long long)lo + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; u <= hi;
+         u += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((unsigned)u);
+        const float ref = logf(x);
+        const float a = log_exact(x);
+        const float2 b = log_exact2(make_float2(x, __uint_as_float((unsigned)(hi - (u - lo)))));
+        bad += (__float_as_uint(a) != __float_as_uint(ref)) + (__float_as_uint(b.x) != __float_as_uint(ref));
+        bad += (__float_as_uint(b.y) != __float_as_uint(logf(__uint_as_float((unsigned)(hi - (u - lo))))));
+    }
+    if (bad) atomicAdd(mism, bad);
+}
+__global__ void selftest_div_kernel(unsigned lo, unsigned hi, float b, unsigned long long* mism) {
+    const float rb = __frcp_rn(b);
+    unsigned long long bad = 0;
+    for (unsigned long long u = (unsigned long long)lo + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; u <= hi;
+         u += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((unsigned)u);
+        bad += (__float_as_uint(div_by_const(x, b, rb)) != __float_as_uint(__fdiv_rn(x, b)));
+        bad += (__float_as_uint(div_by_const(-x, b, rb)) != __float_as_uint(__fdiv_rn(-x, b)));
+    }
+    if (bad) atomicAdd(mism, bad);
+}
+}  // namespace cadl
 
 namespace {
 
@@ -19,6 +48,13 @@ inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? CADL_OK : CADL_ERR
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 thread_local char g_err_detail[256];
+
+inline bool markstein_safe_host(float b) {
+    uint32_t u;
+    memcpy(&u, &b, 4);
+    u &= 0x7fffffffu;
+    return (u >= 0x00800000u) && (u < 0x7f000000u) && ((u & 0x007fffffu) != 0x007fffffu);
+}
 
 struct Ws {
     WsLayout L;
@@ -33,6 +69,7 @@ struct Ws {
 };
 
 constexpr int kPointBlocks = 148 * 8;
+int g_force_generic = 0;   // cadl_debug_force_generic(): tests compare the two phase-B kernels
 
 WsLayout layout_for(int B, int H, int W) {
     WsLayout L = ws_layout(B, H, W);
@@ -86,6 +123,19 @@ cudaError_t launch_tile(const PhaseBArgs& a, cudaStream_t st) {
         configured = true;
     }
     phase_b_tile_kernel<F><<<a.b_rows, kThreadsB, kTileSmemBytes, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int F>
+cudaError_t launch_fast(const PhaseBArgs& a, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(phase_b_fast_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)kFastSmemBytes);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    phase_b_fast_kernel<F><<<a.b_rows, kThreadsB, kFastSmemBytes, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -163,6 +213,20 @@ int run_grad(const float* pred, const float* gt, const float* rgb, const float* 
         }
         return cuda_rc(e);
     }
+    // fast path: aligned shapes (every BASELINE configuration); same values, ~4x fewer instructions
+    const bool fast = a.vec_ok && (H % 8 == 0) && (W % 8 == 0) && (!(t & CADL_TERM_GRAD) || p.num_scales == 4) &&
+                      (!((t & CADL_TERM_SI) && (t & CADL_TERM_GRAD)) || p.eps_si == p.eps_grad) && !g_force_generic;
+    if (fast) {
+        a.tiles_x = (W + FTW - 1) / FTW; a.tiles_y = (H + FTH - 1) / FTH;
+        a.b_rows = a.tiles_x * a.tiles_y * B;
+        switch (t) {
+            case CADL_TERM_ALL: e = launch_fast<15>(a, st); break;
+            case CADL_TERM_SI | CADL_TERM_GRAD | CADL_TERM_SMOOTH: e = launch_fast<7>(a, st); break;
+            case CADL_TERM_GRAD: e = launch_fast<FB_GRAD>(a, st); break;
+            case CADL_TERM_SMOOTH: e = launch_fast<FB_SMOOTH>(a, st); break;
+            default: return CADL_ERR_UNSUPPORTED;
+        }
+    } else {
     a.b_rows = ws.L.b_tiles;
     switch (t) {
         case CADL_TERM_ALL: e = launch_tile<15>(a, st); break;                           // forwardWithIntrinsics
@@ -170,6 +234,7 @@ int run_grad(const float* pred, const float* gt, const float* rgb, const float* 
         case CADL_TERM_GRAD: e = launch_tile<FB_GRAD>(a, st); break;
         case CADL_TERM_SMOOTH: e = launch_tile<FB_SMOOTH>(a, st); break;
         default: return CADL_ERR_UNSUPPORTED;
+    }
     }
     if (e != cudaSuccess) return cuda_rc(e);
     if ((t & CADL_TERM_SMOOTH) && grad) {
@@ -204,6 +269,7 @@ void cadl_default_params(cadl_params* p) {
 }
 
 int cadl_version(void) { return CADL_VERSION; }
+void cadl_debug_force_generic(int on) { g_force_generic = on; }
 size_t cadl_sizeof_params(void) { return sizeof(cadl_params); }
 size_t cadl_sizeof_results(void) { return sizeof(cadl_results); }
 
@@ -352,6 +418,19 @@ int cadl_metrics(const float* pred, const float* gt, const uint8_t* mask, size_t
     p.terms = 0; p.metrics = which; p.min_depth = min_depth; p.max_depth = max_depth;
     return cadl_stack_fwd_bwd(pred, gt, nullptr, nullptr, mask, 1, 1, (int)n, &p, nullptr, results, workspace,
                               workspace_bytes, stream);
+}
+
+int cadl_selftest(int which, uint32_t lo_bits, uint32_t hi_bits, float param, unsigned long long* mismatches_dev,
+                  cadl_stream_t stream) {
+    if (!mismatches_dev) return CADL_ERR_NULL;
+    if (hi_bits < lo_bits) return CADL_ERR_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (which == 0) selftest_log_kernel<<<148 * 8, 256, 0, st>>>(lo_bits, hi_bits, mismatches_dev);
+    else if (which == 1) {
+        if (!markstein_safe_host(param)) return CADL_ERR_UNSUPPORTED;
+        selftest_div_kernel<<<148 * 8, 256, 0, st>>>(lo_bits, hi_bits, param, mismatches_dev);
+    } else return CADL_ERR_UNSUPPORTED;
+    return cuda_rc(cudaGetLastError());
 }
 
 int cadl_rays_from_K(const float* K, int k_batched, const float* pose, int B, int H, int W, int layout,

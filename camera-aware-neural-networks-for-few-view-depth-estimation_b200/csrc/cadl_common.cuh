@@ -65,8 +65,10 @@ constexpr int HALO = 8;   // 2^(CADL_MAX_SCALES-1)
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 __host__ inline int a_blocks_per_image(int B, int HW) {
-    // ~4 blocks per SM over 148 SMs, at least 1024 px per block, each block inside one image
-    int target = (148 * 4 + B - 1) / B;
+    // 8 resident blocks per SM over 148 SMs in (close to) whole waves, at least 1024 px per block,
+    // each block inside one image
+    int target = (148 * 8) / B;
+    if (target < 1) target = 1;
     int by_size = (HW + 1023) / 1024;
     int n = target < by_size ? target : by_size;
     return n < 1 ? 1 : n;
@@ -77,7 +79,7 @@ __host__ inline WsLayout ws_layout(int B, int H, int W) {
     int HW = H * W;
     L.a_blocks_per_img = a_blocks_per_image(B, HW);
     L.a_blocks = L.a_blocks_per_img * B;
-    int tx = (W + TW - 1) / TW, ty = (H + TH - 1) / TH;
+    int tx = (W + TW - 1) / TW, ty = (H + TH - 1) / TH;   // generic tiling (32 x 128) >= fast tiling (48 x 128)
     L.b_tiles = tx * ty * B;
     size_t o = 0;
     L.header = o;   o = align_up(o + sizeof(WsHeader), 256);

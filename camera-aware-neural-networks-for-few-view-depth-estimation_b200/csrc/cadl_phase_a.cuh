@@ -5,6 +5,7 @@
 // block (ticket) reduces the rows in a fixed order (deterministic; no floating-point atomics).
 #pragma once
 #include "cadl_common.cuh"
+#include "cadl_math.cuh"
 
 namespace cadl {
 
@@ -25,17 +26,26 @@ struct PhaseAArgs {
     double* a_part;
 };
 
+// delta-threshold counting with the reference's IEEE semantics at SFU cost: the quotients come from
+// rcp.approx (<= 2 ulp), and only when max(p/g, g/p) lies within a guard band of a threshold (probability
+// ~1e-5 per pixel) are the two IEEE divisions of depth_metrics.h:221 / trainer :433 actually performed.
+__device__ __forceinline__ float ratio_for_thresholds(float p, float g, float rp, float rg) {
+    float ratio = fmaxf(p * rg, g * rp);
+    const bool near = (fabsf(ratio - 1.25f) < 4e-6f) || (fabsf(ratio - 1.5625f) < 5e-6f) ||
+                      (fabsf(ratio - 1.953125f) < 6e-6f) || !(ratio == ratio);
+    if (near) ratio = fmaxf(__fdiv_rn(p, g), __fdiv_rn(g, p));
+    return ratio;
+}
+
+// One pair of pixels (packed fp32x2 logs).  lpv/lgv: logs of clamp(x, eps_si, 1000) when F needs them.
 template <int F>
-__device__ __forceinline__ void phase_a_px(float p, float g, bool has_mask, bool um,
-                                           const PhaseAArgs& a, float (&af)[AF_COUNT],
-                                           unsigned (&ai)[AI_COUNT]) {
+__device__ __forceinline__ void phase_a_px(float p, float g, float lp, float lg, bool has_mask, bool um,
+                                           const PhaseAArgs& a, float (&af)[AF_COUNT], unsigned (&ai)[AI_COUNT]) {
     if constexpr (F & FA_PSUM) af[AF_PSUM] += p;            // depth_loss.h:192 (mean over H,W)
     if constexpr (F & FA_SI) {
         // depth_loss.h:38-47
-        bool m = has_mask ? um : (g > a.eps_si);
-        float pc = clampf(p, a.eps_si, 1000.0f);
-        float gc = clampf(g, a.eps_si, 1000.0f);
-        float d = logf(pc) - logf(gc);
+        const bool m = has_mask ? um : (g > a.eps_si);
+        const float d = lp - lg;
         if (m) {
             ai[AI_SI_N] += 1u;
             af[AF_SI_S] += d;
@@ -43,50 +53,77 @@ __device__ __forceinline__ void phase_a_px(float p, float g, bool has_mask, bool
         }
     }
     if constexpr (F & FA_RP) {
-        bool m = has_mask ? um : (g > a.eps_rp);            // depth_loss.h:318-320
+        const bool m = has_mask ? um : (g > a.eps_rp);      // depth_loss.h:318-320
         if (m) ai[AI_RP_N] += 1u;
     }
-    if constexpr (F & FA_EV) {
-        // depth_metrics.h:154-161 (mask), :66 (clamp after masking), :169-229
-        bool m = (g > a.min_d) && (g < a.max_d) && (has_mask ? um : true);
-        if (m) {
-            float pc = clampf(p, a.min_d, a.max_d);
-            float diff = pc - g;
-            float ad = fabsf(diff);
-            float sq = diff * diff;                          // torch::pow(x, 2) == x*x
-            af[AF_EV_ABSREL] += ad / g;
-            af[AF_EV_SQREL] += sq / g;
-            af[AF_EV_SQ] += sq;
-            float ld = logf(pc) - logf(g);
-            af[AF_EV_LOGSQ] += ld * ld;
-            af[AF_EV_ABS] += ad;
-            af[AF_EV_LOG10] += fabsf(log10f(pc) - log10f(g));
-            float ratio = fmaxf(pc / g, g / pc);
-            ai[AI_EV_N] += 1u;
-            ai[AI_EV_C1] += (ratio < 1.25f) ? 1u : 0u;
-            ai[AI_EV_C2] += (ratio < 1.25f * 1.25f) ? 1u : 0u;
-            ai[AI_EV_C3] += (ratio < 1.25f * 1.25f * 1.25f) ? 1u : 0u;
-            af[AF_EV_SUMP] += pc;
-            af[AF_EV_SUMG] += g;
+    if constexpr ((F & (FA_EV | FA_TR)) != 0) {
+        // Both metric variants share their per-pixel terms whenever clamping leaves pred unchanged and
+        // x + 1e-8f == x; the general (rare) cases are evaluated separately below.
+        const float pc = clamp_nan(p, a.min_d, a.max_d);                       // depth_metrics.h:66
+        const float psi = clamp_nan(p, a.eps_si, 1000.0f), gsi = clamp_nan(g, a.eps_si, 1000.0f);
+        const bool ev_ok = (F & FA_EV) && (g > a.min_d) && (g < a.max_d) && (has_mask ? um : true);   // :154-161
+        const bool tr_ok = (F & FA_TR) && (g > 0.0f);                          // trainer :410
+        if (ev_ok || tr_ok) {
+            const float rg = rcp_approx(g);
+            // ---- eval terms (pred clamped) ----
+            const float lpc = (pc == psi) ? lp : logf(pc);
+            const float lge = (g == gsi) ? lg : logf(g);
+            const float diff = pc - g, ad = fabsf(diff), sq = diff * diff;     // torch::pow(x,2) == x*x
+            const float ld = lpc - lge;
+            const float ratio = ratio_for_thresholds(pc, g, rcp_approx(pc), rg);
+            if (ev_ok) {
+                af[AF_EV_ABSREL] += ad * rg;                                   // :170
+                af[AF_EV_SQREL] += sq * rg;                                    // :177
+                af[AF_EV_SQ] += sq;                                            // :184
+                af[AF_EV_LOGSQ] += ld * ld;                                    // :191-192
+                af[AF_EV_ABS] += ad;                                           // :199
+                af[AF_EV_LOG10] += fabsf(ld) * 0.43429448190325182765f;        // :206 (log10 x = ln x / ln 10)
+                ai[AI_EV_N] += 1u;
+                ai[AI_EV_C1] += (ratio < 1.25f) ? 1u : 0u;                     // :224-229
+                ai[AI_EV_C2] += (ratio < 1.25f * 1.25f) ? 1u : 0u;
+                ai[AI_EV_C3] += (ratio < 1.25f * 1.25f * 1.25f) ? 1u : 0u;
+                af[AF_EV_SUMP] += pc;                                          // :84
+                af[AF_EV_SUMG] += g;                                           // :85
+            }
+            if (tr_ok) {
+                // trainer :419-436: no clamp, log(x + 1e-8)
+                const float p8 = p + 1e-8f, g8 = g + 1e-8f;
+                float adt = ad, sqt = sq, ldt = ld, rt = ratio;
+                if (!(pc == p) || !(p8 == psi) || !(g8 == gsi)) {              // rare: recompute unshared
+                    adt = fabsf(p - g);
+                    sqt = adt * adt;
+                    ldt = logf(p8) - logf(g8);
+                    rt = fmaxf(__fdiv_rn(p, g), __fdiv_rn(g, p));
+                }
+                af[AF_TR_ABSREL] += adt * rg;
+                af[AF_TR_SQREL] += sqt * rg;
+                af[AF_TR_SQ] += sqt;
+                af[AF_TR_LOGSQ] += ldt * ldt;
+                ai[AI_TR_N] += 1u;
+                ai[AI_TR_C1] += (rt < 1.25f) ? 1u : 0u;
+                ai[AI_TR_C2] += (rt < 1.5625f) ? 1u : 0u;
+                ai[AI_TR_C3] += (rt < 1.953125f) ? 1u : 0u;
+            }
         }
     }
-    if constexpr (F & FA_TR) {
-        // tensorboard_trainer_enhanced.h:410-436
-        if (g > 0.0f) {
-            float ad = fabsf(p - g);
-            float sq = ad * ad;
-            af[AF_TR_ABSREL] += ad / g;
-            af[AF_TR_SQREL] += sq / g;
-            af[AF_TR_SQ] += sq;
-            float ld = fabsf(logf(p + 1e-8f) - logf(g + 1e-8f));
-            af[AF_TR_LOGSQ] += ld * ld;
-            float ratio = fmaxf(p / g, g / p);
-            ai[AI_TR_N] += 1u;
-            ai[AI_TR_C1] += (ratio < 1.25f) ? 1u : 0u;
-            ai[AI_TR_C2] += (ratio < 1.5625f) ? 1u : 0u;
-            ai[AI_TR_C3] += (ratio < 1.953125f) ? 1u : 0u;
+}
+
+template <int F>
+__device__ __forceinline__ void phase_a_quad(const float (&p)[4], const float (&g)[4], bool has_mask,
+                                             const bool (&um)[4], const PhaseAArgs& a, float (&af)[AF_COUNT],
+                                             unsigned (&ai)[AI_COUNT]) {
+    float lp[4] = {0.f, 0.f, 0.f, 0.f}, lg[4] = {0.f, 0.f, 0.f, 0.f};
+    if constexpr ((F & (FA_SI | FA_EV | FA_TR)) != 0) {
+#pragma unroll
+        for (int k = 0; k < 4; k += 2) {
+            const float2 a2 = log_exact2(make_float2(clamp_nan(p[k], a.eps_si, 1000.0f), clamp_nan(p[k + 1], a.eps_si, 1000.0f)));
+            const float2 b2 = log_exact2(make_float2(clamp_nan(g[k], a.eps_si, 1000.0f), clamp_nan(g[k + 1], a.eps_si, 1000.0f)));
+            lp[k] = a2.x; lp[k + 1] = a2.y;
+            lg[k] = b2.x; lg[k + 1] = b2.y;
         }
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) phase_a_px<F>(p[k], g[k], lp[k], lg[k], has_mask, um[k], a, af, ai);
 }
 
 // Deterministic block-wide sum of one double per thread (fixed shuffle/tree order).
@@ -141,15 +178,15 @@ __global__ void __launch_bounds__(kThreadsA) phase_a_kernel(const PhaseAArgs a) 
             if (NEED_P) { p0 = __ldg(p4 + i); if (hj) p1 = __ldg(p4 + j); }
             if (NEED_G) { g0 = __ldg(g4 + i); if (hj) g1 = __ldg(g4 + j); }
             if (has_mask) { u0 = __ldg(m4 + i); if (hj) u1 = __ldg(m4 + j); }
-            phase_a_px<F>(p0.x, g0.x, has_mask, u0.x != 0, a, af, ai);
-            phase_a_px<F>(p0.y, g0.y, has_mask, u0.y != 0, a, af, ai);
-            phase_a_px<F>(p0.z, g0.z, has_mask, u0.z != 0, a, af, ai);
-            phase_a_px<F>(p0.w, g0.w, has_mask, u0.w != 0, a, af, ai);
+            {
+                const float pp[4] = {p0.x, p0.y, p0.z, p0.w}, gg[4] = {g0.x, g0.y, g0.z, g0.w};
+                const bool mm[4] = {u0.x != 0, u0.y != 0, u0.z != 0, u0.w != 0};
+                phase_a_quad<F>(pp, gg, has_mask, mm, a, af, ai);
+            }
             if (hj) {
-                phase_a_px<F>(p1.x, g1.x, has_mask, u1.x != 0, a, af, ai);
-                phase_a_px<F>(p1.y, g1.y, has_mask, u1.y != 0, a, af, ai);
-                phase_a_px<F>(p1.z, g1.z, has_mask, u1.z != 0, a, af, ai);
-                phase_a_px<F>(p1.w, g1.w, has_mask, u1.w != 0, a, af, ai);
+                const float pp[4] = {p1.x, p1.y, p1.z, p1.w}, gg[4] = {g1.x, g1.y, g1.z, g1.w};
+                const bool mm[4] = {u1.x != 0, u1.y != 0, u1.z != 0, u1.w != 0};
+                phase_a_quad<F>(pp, gg, has_mask, mm, a, af, ai);
             }
         }
     } else {
@@ -159,7 +196,12 @@ __global__ void __launch_bounds__(kThreadsA) phase_a_kernel(const PhaseAArgs a) 
             float p = NEED_P ? __ldg(a.pred + base + i) : 0.f;
             float g = NEED_G ? __ldg(a.gt + base + i) : 0.f;
             bool um = has_mask ? (__ldg(a.mask + base + i) != 0) : true;
-            phase_a_px<F>(p, g, has_mask, um, a, af, ai);
+            float lp = 0.f, lg = 0.f;
+            if constexpr ((F & (FA_SI | FA_EV | FA_TR)) != 0) {
+                lp = log_exact(clamp_nan(p, a.eps_si, 1000.0f));
+                lg = log_exact(clamp_nan(g, a.eps_si, 1000.0f));
+            }
+            phase_a_px<F>(p, g, lp, lg, has_mask, um, a, af, ai);
         }
     }
 

@@ -93,6 +93,14 @@ int cadl_version(void);
 size_t cadl_sizeof_params(void);
 size_t cadl_sizeof_results(void);
 const char* cadl_error_string(int code);
+/* Test hook: 1 = always take the generic phase-B kernel (any shape/alignment) instead of the aligned
+ * fast path; both must produce the same values.  Process-global; not for production use. */
+void cadl_debug_force_generic(int on);
+/* Test hook: counts (into *mismatches_dev, a device uint64 the caller zeroed) the inputs with bit pattern in
+ * [lo_bits, hi_bits] for which a device-math replica differs from the CUDA library form.
+ *   which 0: log replica (scalar and packed fp32x2) vs logf;  which 1: Markstein a/param vs IEEE division. */
+int cadl_selftest(int which, uint32_t lo_bits, uint32_t hi_bits, float param, unsigned long long* mismatches_dev,
+                  cadl_stream_t stream);
 
 /* Bytes of workspace for a (B,H,W) problem; 256-byte aligned pointer required.  The workspace must
  * be zeroed ONCE (cadl_workspace_init) and is left clean by every call. */

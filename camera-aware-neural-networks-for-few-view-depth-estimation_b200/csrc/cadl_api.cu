@@ -97,7 +97,8 @@ uint32_t phase_a_flags(const cadl_params& p) {
 
 template <int F>
 cudaError_t launch_a(const PhaseAArgs& a, dim3 grid, cudaStream_t st) {
-    phase_a_kernel<F><<<grid, kThreadsA, 0, st>>>(a);
+    if (a.mask) phase_a_kernel<F, true><<<grid, kThreadsA, 0, st>>>(a);
+    else phase_a_kernel<F, false><<<grid, kThreadsA, 0, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -126,17 +127,21 @@ cudaError_t launch_tile(const PhaseBArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-template <int F>
-cudaError_t launch_fast(const PhaseBArgs& a, cudaStream_t st) {
+template <int F, bool M>
+cudaError_t launch_fast_m(const PhaseBArgs& a, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(phase_b_fast_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(phase_b_fast_kernel<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)kFastSmemBytes);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    phase_b_fast_kernel<F><<<a.b_rows, kThreadsB, kFastSmemBytes, st>>>(a);
+    phase_b_fast_kernel<F, M><<<a.b_rows, kThreadsB, kFastSmemBytes, st>>>(a);
     return cudaGetLastError();
+}
+template <int F>
+cudaError_t launch_fast(const PhaseBArgs& a, cudaStream_t st) {
+    return a.mask ? launch_fast_m<F, true>(a, st) : launch_fast_m<F, false>(a, st);
 }
 
 template <int F>
@@ -159,6 +164,9 @@ int run_reduce(const float* pred, const float* gt, const uint8_t* mask, int B, i
     a.vec_ok = ((H * W) % 4 == 0) && (!pred || aligned(pred, 16)) && (!gt || aligned(gt, 16)) &&
                (!mask || aligned(mask, 4));
     a.eps_si = p.eps_si; a.eps_rp = p.eps_reproj; a.min_d = p.min_depth; a.max_d = p.max_depth;
+    a.g_lo = p.min_depth > 0.25f ? p.min_depth : 0.25f;
+    a.p_lo = a.g_lo;
+    a.share_ok = (p.eps_si <= p.min_depth) && (p.max_depth <= 1000.0f) && (p.min_depth > 0.0f);
     a.hdr = ws.hdr(); a.stats = ws.stats(); a.img_psum = ws.img_psum(); a.a_part = ws.a_part();
     dim3 grid(a.blocks_per_img, B);
     return cuda_rc(dispatch_a(f, a, grid, st));
@@ -201,6 +209,14 @@ int run_grad(const float* pred, const float* gt, const float* rgb, const float* 
     a.stats = ws.stats(); a.img_psum = ws.img_psum(); a.b_part = ws.b_part();
     a.hdr = ws.hdr(); a.img_sm = ws.img_sm(); a.img_off = ws.img_off();
     a.results = results;
+    for (int s = 0; s < 4; ++s) {
+        const int Hs = H >> s, Ws = W >> s;
+        const double nx = (double)a.global_B * Hs * (Ws - 1), ny = (double)a.global_B * (Hs - 1) * Ws;
+        a.inv_nx[s] = nx > 0.0 ? (float)(1.0 / nx) : 0.f;
+        a.inv_ny[s] = ny > 0.0 ? (float)(1.0 / ny) : 0.f;
+    }
+    a.sm_nx = a.inv_nx[0];
+    a.sm_ny = a.inv_ny[0];
 
     cudaError_t e = cudaSuccess;
     if ((t & (CADL_TERM_GRAD | CADL_TERM_SMOOTH)) == 0) {
@@ -215,7 +231,8 @@ int run_grad(const float* pred, const float* gt, const float* rgb, const float* 
     }
     // fast path: aligned shapes (every BASELINE configuration); same values, ~4x fewer instructions
     const bool fast = a.vec_ok && (H % 8 == 0) && (W % 8 == 0) && (!(t & CADL_TERM_GRAD) || p.num_scales == 4) &&
-                      (!((t & CADL_TERM_SI) && (t & CADL_TERM_GRAD)) || p.eps_si == p.eps_grad) && !g_force_generic;
+                      (!((t & CADL_TERM_SI) && (t & CADL_TERM_GRAD)) || p.eps_si == p.eps_grad) && p.eps_si > 0.f &&
+                      p.eps_grad > 0.f && p.eps_si <= 1000.f && p.eps_grad <= 1000.f && !g_force_generic;
     if (fast) {
         a.tiles_x = (W + FTW - 1) / FTW; a.tiles_y = (H + FTH - 1) / FTH;
         a.b_rows = a.tiles_x * a.tiles_y * B;

@@ -20,6 +20,8 @@ struct PhaseAArgs {
     int blocks_per_img;
     int vec_ok;
     float eps_si, eps_rp, min_d, max_d;
+    float g_lo, p_lo;    // fast-metrics thresholds: max(min_d, 0.25)
+    int share_ok;        // eps_si <= min_d && max_d <= 1000: both metric variants can reuse the SI logs
     WsHeader* hdr;
     double* stats;
     double* img_psum;
@@ -37,93 +39,126 @@ __device__ __forceinline__ float ratio_for_thresholds(float p, float g, float rp
     return ratio;
 }
 
-// One pair of pixels (packed fp32x2 logs).  lpv/lgv: logs of clamp(x, eps_si, 1000) when F needs them.
-template <int F>
-__device__ __forceinline__ void phase_a_px(float p, float g, float lp, float lg, bool has_mask, bool um,
-                                           const PhaseAArgs& a, float (&af)[AF_COUNT], unsigned (&ai)[AI_COUNT]) {
-    if constexpr (F & FA_PSUM) af[AF_PSUM] += p;            // depth_loss.h:192 (mean over H,W)
+// Per-thread accumulators of phase A.  Both metric variants take the same per-pixel terms whenever
+// min < gt < max, pred needs no clamping and x + 1e-8f == x (x >= 0.25): those pixels go to ONE set of
+// "common" accumulators; the few others are evaluated separately per variant (slow path).
+struct AccA {
+    float psum, si_s, si_q;
+    unsigned si_n, rp_n;
+    float c_absrel, c_sqrel, c_sq, c_logsq;          // common to eval and train
+    unsigned c_n, c_c1, c_c2, c_c3;
+    float e_abs, e_l10, e_sump, e_sumg;              // eval-only quantities
+    float eo_absrel, eo_sqrel, eo_sq, eo_logsq;      // eval, slow path
+    unsigned eo_n, eo_c1, eo_c2, eo_c3;
+    float to_absrel, to_sqrel, to_sq, to_logsq;      // train, slow path
+    unsigned to_n, to_c1, to_c2, to_c3;
+};
+
+template <int F, bool HAS_MASK>
+__device__ __forceinline__ void phase_a_px(float p, float g, float psi, float gsi, float lp, float lg, bool um,
+                                           const PhaseAArgs& a, AccA& A) {
+    if constexpr (F & FA_PSUM) A.psum += p;                 // depth_loss.h:192 (mean over H,W)
     if constexpr (F & FA_SI) {
         // depth_loss.h:38-47
-        const bool m = has_mask ? um : (g > a.eps_si);
+        const bool m = HAS_MASK ? um : (g > a.eps_si);
         const float d = lp - lg;
         if (m) {
-            ai[AI_SI_N] += 1u;
-            af[AF_SI_S] += d;
-            af[AF_SI_Q] += d * d;
+            A.si_n += 1u;
+            A.si_s += d;
+            A.si_q = fmaf(d, d, A.si_q);
         }
     }
     if constexpr (F & FA_RP) {
-        const bool m = has_mask ? um : (g > a.eps_rp);      // depth_loss.h:318-320
-        if (m) ai[AI_RP_N] += 1u;
+        const bool m = HAS_MASK ? um : (g > a.eps_rp);      // depth_loss.h:318-320
+        if (m) A.rp_n += 1u;
     }
     if constexpr ((F & (FA_EV | FA_TR)) != 0) {
-        // Both metric variants share their per-pixel terms whenever clamping leaves pred unchanged and
-        // x + 1e-8f == x; the general (rare) cases are evaluated separately below.
-        const float pc = clamp_nan(p, a.min_d, a.max_d);                       // depth_metrics.h:66
-        const float psi = clamp_nan(p, a.eps_si, 1000.0f), gsi = clamp_nan(g, a.eps_si, 1000.0f);
-        const bool ev_ok = (F & FA_EV) && (g > a.min_d) && (g < a.max_d) && (has_mask ? um : true);   // :154-161
-        const bool tr_ok = (F & FA_TR) && (g > 0.0f);                          // trainer :410
-        if (ev_ok || tr_ok) {
-            const float rg = rcp_approx(g);
-            // ---- eval terms (pred clamped) ----
-            const float lpc = (pc == psi) ? lp : logf(pc);
-            const float lge = (g == gsi) ? lg : logf(g);
-            const float diff = pc - g, ad = fabsf(diff), sq = diff * diff;     // torch::pow(x,2) == x*x
-            const float ld = lpc - lge;
-            const float ratio = ratio_for_thresholds(pc, g, rcp_approx(pc), rg);
+        constexpr bool EV = (F & FA_EV) != 0, TR = (F & FA_TR) != 0;
+        const bool fast = a.share_ok && (g > a.g_lo) && (g < a.max_d) && (p >= a.p_lo) && (p <= a.max_d) &&
+                          (HAS_MASK ? um : true);
+        if (fast) {
+            // min < g < max, no clamp, +1e-8 is a no-op: lp, lg are exactly the logs both variants use
+            const float rg = rcp_approx(g), rp = rcp_approx(p);
+            const float diff = p - g, ad = fabsf(diff), sq = diff * diff;          // depth_metrics.h:170-199
+            const float ld = lp - lg;
+            const float ratio = ratio_for_thresholds(p, g, rp, rg);                 // :221
+            A.c_absrel = fmaf(ad, rg, A.c_absrel);
+            A.c_sqrel = fmaf(sq, rg, A.c_sqrel);
+            A.c_sq += sq;
+            A.c_logsq = fmaf(ld, ld, A.c_logsq);
+            A.c_n += 1u;
+            A.c_c1 += (ratio < 1.25f) ? 1u : 0u;                                    // :224-229, trainer :434-436
+            A.c_c2 += (ratio < 1.5625f) ? 1u : 0u;
+            A.c_c3 += (ratio < 1.953125f) ? 1u : 0u;
+            if constexpr (EV) {
+                A.e_abs += ad;
+                A.e_l10 += fabsf(ld);                                               // x log10(e) at the end (:206)
+                A.e_sump += p;
+                A.e_sumg += g;
+            }
+        } else {
+            const bool ev_ok = EV && (g > a.min_d) && (g < a.max_d) && (HAS_MASK ? um : true);   // :154-161
+            const bool tr_ok = TR && (g > 0.0f);                                                  // trainer :410
             if (ev_ok) {
-                af[AF_EV_ABSREL] += ad * rg;                                   // :170
-                af[AF_EV_SQREL] += sq * rg;                                    // :177
-                af[AF_EV_SQ] += sq;                                            // :184
-                af[AF_EV_LOGSQ] += ld * ld;                                    // :191-192
-                af[AF_EV_ABS] += ad;                                           // :199
-                af[AF_EV_LOG10] += fabsf(ld) * 0.43429448190325182765f;        // :206 (log10 x = ln x / ln 10)
-                ai[AI_EV_N] += 1u;
-                ai[AI_EV_C1] += (ratio < 1.25f) ? 1u : 0u;                     // :224-229
-                ai[AI_EV_C2] += (ratio < 1.25f * 1.25f) ? 1u : 0u;
-                ai[AI_EV_C3] += (ratio < 1.25f * 1.25f * 1.25f) ? 1u : 0u;
-                af[AF_EV_SUMP] += pc;                                          // :84
-                af[AF_EV_SUMG] += g;                                           // :85
+                const float pc = clamp_nan(p, a.min_d, a.max_d);                    // :66
+                const float diff = pc - g, ad = fabsf(diff), sq = diff * diff;
+                const float ld = logf(pc) - logf(g);
+                const float ratio = fmaxf(__fdiv_rn(pc, g), __fdiv_rn(g, pc));
+                const float rg = rcp_approx(g);
+                A.eo_absrel = fmaf(ad, rg, A.eo_absrel);
+                A.eo_sqrel = fmaf(sq, rg, A.eo_sqrel);
+                A.eo_sq += sq;
+                A.eo_logsq = fmaf(ld, ld, A.eo_logsq);
+                A.eo_n += 1u;
+                A.eo_c1 += (ratio < 1.25f) ? 1u : 0u;
+                A.eo_c2 += (ratio < 1.25f * 1.25f) ? 1u : 0u;
+                A.eo_c3 += (ratio < 1.25f * 1.25f * 1.25f) ? 1u : 0u;
+                A.e_abs += ad;
+                A.e_l10 += fabsf(ld);
+                A.e_sump += pc;
+                A.e_sumg += g;
             }
             if (tr_ok) {
                 // trainer :419-436: no clamp, log(x + 1e-8)
-                const float p8 = p + 1e-8f, g8 = g + 1e-8f;
-                float adt = ad, sqt = sq, ldt = ld, rt = ratio;
-                if (!(pc == p) || !(p8 == psi) || !(g8 == gsi)) {              // rare: recompute unshared
-                    adt = fabsf(p - g);
-                    sqt = adt * adt;
-                    ldt = logf(p8) - logf(g8);
-                    rt = fmaxf(__fdiv_rn(p, g), __fdiv_rn(g, p));
-                }
-                af[AF_TR_ABSREL] += adt * rg;
-                af[AF_TR_SQREL] += sqt * rg;
-                af[AF_TR_SQ] += sqt;
-                af[AF_TR_LOGSQ] += ldt * ldt;
-                ai[AI_TR_N] += 1u;
-                ai[AI_TR_C1] += (rt < 1.25f) ? 1u : 0u;
-                ai[AI_TR_C2] += (rt < 1.5625f) ? 1u : 0u;
-                ai[AI_TR_C3] += (rt < 1.953125f) ? 1u : 0u;
+                const float adt = fabsf(p - g), sqt = adt * adt;
+                const float ldt = logf(p + 1e-8f) - logf(g + 1e-8f);
+                const float rt = fmaxf(__fdiv_rn(p, g), __fdiv_rn(g, p));
+                const float rg = rcp_approx(g);
+                A.to_absrel = fmaf(adt, rg, A.to_absrel);
+                A.to_sqrel = fmaf(sqt, rg, A.to_sqrel);
+                A.to_sq += sqt;
+                A.to_logsq = fmaf(ldt, ldt, A.to_logsq);
+                A.to_n += 1u;
+                A.to_c1 += (rt < 1.25f) ? 1u : 0u;
+                A.to_c2 += (rt < 1.5625f) ? 1u : 0u;
+                A.to_c3 += (rt < 1.953125f) ? 1u : 0u;
             }
         }
     }
+    (void)psi; (void)gsi;
 }
 
-template <int F>
-__device__ __forceinline__ void phase_a_quad(const float (&p)[4], const float (&g)[4], bool has_mask,
-                                             const bool (&um)[4], const PhaseAArgs& a, float (&af)[AF_COUNT],
-                                             unsigned (&ai)[AI_COUNT]) {
+template <int F, bool HAS_MASK>
+__device__ __forceinline__ void phase_a_quad(const float (&p)[4], const float (&g)[4], const bool (&um)[4],
+                                             const PhaseAArgs& a, AccA& A) {
     float lp[4] = {0.f, 0.f, 0.f, 0.f}, lg[4] = {0.f, 0.f, 0.f, 0.f};
+    float psi[4] = {0.f, 0.f, 0.f, 0.f}, gsi[4] = {0.f, 0.f, 0.f, 0.f};
     if constexpr ((F & (FA_SI | FA_EV | FA_TR)) != 0) {
 #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            psi[k] = clamp_nan(p[k], a.eps_si, 1000.0f);     // depth_loss.h:43-44
+            gsi[k] = clamp_nan(g[k], a.eps_si, 1000.0f);
+        }
+#pragma unroll
         for (int k = 0; k < 4; k += 2) {
-            const float2 a2 = log_exact2(make_float2(clamp_nan(p[k], a.eps_si, 1000.0f), clamp_nan(p[k + 1], a.eps_si, 1000.0f)));
-            const float2 b2 = log_exact2(make_float2(clamp_nan(g[k], a.eps_si, 1000.0f), clamp_nan(g[k + 1], a.eps_si, 1000.0f)));
+            const float2 a2 = log_exact2(make_float2(psi[k], psi[k + 1]));
+            const float2 b2 = log_exact2(make_float2(gsi[k], gsi[k + 1]));
             lp[k] = a2.x; lp[k + 1] = a2.y;
             lg[k] = b2.x; lg[k + 1] = b2.y;
         }
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) phase_a_px<F>(p[k], g[k], lp[k], lg[k], has_mask, um[k], a, af, ai);
+    for (int k = 0; k < 4; ++k) phase_a_px<F, HAS_MASK>(p[k], g[k], psi[k], gsi[k], lp[k], lg[k], um[k], a, A);
 }
 
 // Deterministic block-wide sum of one double per thread (fixed shuffle/tree order).
@@ -141,7 +176,7 @@ __device__ __forceinline__ double block_sum_double(double v, double* scratch /*>
     return r;  // valid in warp 0
 }
 
-template <int F>
+template <int F, bool HAS_MASK>
 __global__ void __launch_bounds__(kThreadsA) phase_a_kernel(const PhaseAArgs a) {
     constexpr bool NEED_P = (F & (FA_SI | FA_PSUM | FA_EV | FA_TR)) != 0;
     constexpr bool NEED_G = (F & (FA_SI | FA_RP | FA_EV | FA_TR)) != 0;
@@ -152,15 +187,11 @@ __global__ void __launch_bounds__(kThreadsA) phase_a_kernel(const PhaseAArgs a) 
 
     const int b = blockIdx.y, k = blockIdx.x;
     const int tid = threadIdx.x;
-    const bool has_mask = a.mask != nullptr;
+    constexpr bool has_mask = HAS_MASK;
     const size_t base = (size_t)b * a.HW;
 
-    float af[AF_COUNT];
-    unsigned ai[AI_COUNT];
-#pragma unroll
-    for (int q = 0; q < AF_COUNT; ++q) af[q] = 0.f;
-#pragma unroll
-    for (int q = 0; q < AI_COUNT; ++q) ai[q] = 0u;
+    AccA A;
+    memset(&A, 0, sizeof(A));
     if (tid < AI_COUNT) s_i[tid] = 0u;
 
     if (a.vec_ok) {
@@ -181,12 +212,12 @@ __global__ void __launch_bounds__(kThreadsA) phase_a_kernel(const PhaseAArgs a) 
             {
                 const float pp[4] = {p0.x, p0.y, p0.z, p0.w}, gg[4] = {g0.x, g0.y, g0.z, g0.w};
                 const bool mm[4] = {u0.x != 0, u0.y != 0, u0.z != 0, u0.w != 0};
-                phase_a_quad<F>(pp, gg, has_mask, mm, a, af, ai);
+                phase_a_quad<F, HAS_MASK>(pp, gg, mm, a, A);
             }
             if (hj) {
                 const float pp[4] = {p1.x, p1.y, p1.z, p1.w}, gg[4] = {g1.x, g1.y, g1.z, g1.w};
                 const bool mm[4] = {u1.x != 0, u1.y != 0, u1.z != 0, u1.w != 0};
-                phase_a_quad<F>(pp, gg, has_mask, mm, a, af, ai);
+                phase_a_quad<F, HAS_MASK>(pp, gg, mm, a, A);
             }
         }
     } else {
@@ -196,14 +227,33 @@ __global__ void __launch_bounds__(kThreadsA) phase_a_kernel(const PhaseAArgs a) 
             float p = NEED_P ? __ldg(a.pred + base + i) : 0.f;
             float g = NEED_G ? __ldg(a.gt + base + i) : 0.f;
             bool um = has_mask ? (__ldg(a.mask + base + i) != 0) : true;
-            float lp = 0.f, lg = 0.f;
+            float lp = 0.f, lg = 0.f, psi = 0.f, gsi = 0.f;
             if constexpr ((F & (FA_SI | FA_EV | FA_TR)) != 0) {
-                lp = log_exact(clamp_nan(p, a.eps_si, 1000.0f));
-                lg = log_exact(clamp_nan(g, a.eps_si, 1000.0f));
+                psi = clamp_nan(p, a.eps_si, 1000.0f);
+                gsi = clamp_nan(g, a.eps_si, 1000.0f);
+                lp = log_exact(psi);
+                lg = log_exact(gsi);
             }
-            phase_a_px<F>(p, g, lp, lg, has_mask, um, a, af, ai);
+            phase_a_px<F, HAS_MASK>(p, g, psi, gsi, lp, lg, um, a, A);
         }
     }
+
+    // ---- fold the common / slow-path accumulators into the per-variant sums ----
+    float af[AF_COUNT];
+    unsigned ai[AI_COUNT];
+    af[AF_SI_S] = A.si_s; af[AF_SI_Q] = A.si_q; af[AF_PSUM] = A.psum;
+    af[AF_EV_ABSREL] = A.c_absrel + A.eo_absrel; af[AF_EV_SQREL] = A.c_sqrel + A.eo_sqrel;
+    af[AF_EV_SQ] = A.c_sq + A.eo_sq; af[AF_EV_LOGSQ] = A.c_logsq + A.eo_logsq;
+    af[AF_EV_ABS] = A.e_abs; af[AF_EV_LOG10] = A.e_l10 * 0.43429448190325182765f;   // log10 x = ln x / ln 10
+    af[AF_EV_SUMP] = A.e_sump; af[AF_EV_SUMG] = A.e_sumg;
+    af[AF_TR_ABSREL] = A.c_absrel + A.to_absrel; af[AF_TR_SQREL] = A.c_sqrel + A.to_sqrel;
+    af[AF_TR_SQ] = A.c_sq + A.to_sq; af[AF_TR_LOGSQ] = A.c_logsq + A.to_logsq;
+    ai[AI_SI_N] = A.si_n; ai[AI_RP_N] = A.rp_n;
+    constexpr unsigned ev = (F & FA_EV) ? 1u : 0u, tr = (F & FA_TR) ? 1u : 0u;
+    ai[AI_EV_N] = ev * A.c_n + A.eo_n; ai[AI_EV_C1] = ev * A.c_c1 + A.eo_c1;
+    ai[AI_EV_C2] = ev * A.c_c2 + A.eo_c2; ai[AI_EV_C3] = ev * A.c_c3 + A.eo_c3;
+    ai[AI_TR_N] = tr * A.c_n + A.to_n; ai[AI_TR_C1] = tr * A.c_c1 + A.to_c1;
+    ai[AI_TR_C2] = tr * A.c_c2 + A.to_c2; ai[AI_TR_C3] = tr * A.c_c3 + A.to_c3;
 
     // ---- block reduction: fp32 warp shuffle, then fp64 across warps in warp order ----
     const int warp = tid >> 5, lane = tid & 31;

@@ -39,6 +39,8 @@ struct PhaseBArgs {
     double* img_sm;
     float* img_off;
     cadl_results* results;
+    // host-computed 1/N of the means (depth_loss.h:162-163, :230-231); 0 where a mean has no element
+    float inv_nx[4], inv_ny[4], sm_nx, sm_ny;
 };
 
 // ---- shared-memory geometry of the tile kernel -------------------------------------------------

@@ -103,16 +103,52 @@ __device__ __forceinline__ void pool_scale(const float (&v)[8][8], const PhaseBA
             if (t == 0 && cy >= 0 && cy < (FTH >> S) && cx >= 0 && cx < (FTW >> S)) {
                 const float qq = q[ci][cj];
                 const bool cm = (qq >= a.eps_grad) && (qq <= 1000.0f);
-                cc[fcc_off(S) + cy * fcc_w(S) + cx] = (valid && cm) ? (1.0f / qq) : 0.f;
+                cc[fcc_off(S) + cy * fcc_w(S) + cx] = (valid && cm) ? rcp_approx(qq) : 0.f;
             }
         }
 }
 
-template <int F>
+// One scale's per-cell coefficient pass: every cell evaluates its four edges (the two it owns also feed the
+// loss sum) and stores coefficient * (1/q) * spread [+ the two coarser scales when GATHER].
+template <int S, bool GATHER>
+__device__ __forceinline__ void coef_pass(const PhaseBArgs& a, const FastSmem& sm, int tid, int y0, int x0, float spread,
+                                          float& acc_x, float& acc_y) {
+    constexpr int ch = FTH >> S, cw = FTW >> S, pw = (FTW >> S) + 2;
+    const int Hs = a.H >> S, Ws = a.W >> S;
+    const float inv_nx = a.inv_nx[S], inv_ny = a.inv_ny[S];
+    const float* PL = sm.pl + fpool_off(S);
+    const float* PG = sm.pg + fpool_off(S);
+    float* CC = sm.cc + fcc_off(S);
+    const float* C2 = sm.cc + fcc_off(2);
+    const float* C3 = sm.cc + fcc_off(3);
+    float ax = 0.f, ay = 0.f;
+    for (int i = tid; i < ch * cw; i += kThreadsB) {
+        const int cy = i / cw, cx = i - cy * cw;
+        const int gyc = (y0 >> S) + cy, gxc = (x0 >> S) + cx;
+        float coef = 0.f;
+        if (gyc < Hs && gxc < Ws) {
+            const int c = (cy + 1) * pw + (cx + 1);
+            const float lp = PL[c], lg = PG[c];
+            float sx_r = 0.f, sx_l = 0.f, sy_d = 0.f, sy_u = 0.f;
+            if (gxc + 1 < Ws) { const float e = (PL[c + 1] - lp) - (PG[c + 1] - lg); ax += fabsf(e); sx_r = sgn3(e); }   // :140-148,162
+            if (gxc >= 1) sx_l = sgn3((lp - PL[c - 1]) - (lg - PG[c - 1]));
+            if (gyc + 1 < Hs) { const float e = (PL[c + pw] - lp) - (PG[c + pw] - lg); ay += fabsf(e); sy_d = sgn3(e); } // :151-159,163
+            if (gyc >= 1) sy_u = sgn3((lp - PL[c - pw]) - (lg - PG[c - pw]));
+            coef = ((sx_l - sx_r) * inv_nx + (sy_u - sy_d) * inv_ny) * CC[i] * spread;
+            if constexpr (GATHER) coef += C2[(cy >> 1) * fcc_w(2) + (cx >> 1)] + C3[(cy >> 2) * fcc_w(3) + (cx >> 2)];
+        }
+        CC[i] = coef;
+    }
+    acc_x += ax;
+    acc_y += ay;
+}
+
+template <int F, bool HAS_MASK>
 __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseBArgs a) {
     extern __shared__ __align__(16) float smem_raw[];
     __shared__ float s_f[kThreadsB / 32][BF_COUNT];
     __shared__ double s_d[8];
+    __shared__ float s_c[8];
     __shared__ int s_last;
     FastSmem sm;
     sm.sp = smem_raw;
@@ -133,35 +169,48 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
     const int b = tile / (a.tiles_x * a.tiles_y);
     const int x0 = tx * FTW, y0 = ty * FTH;
     const int H = a.H, W = a.W;
-    const size_t img = (size_t)b * H * W;
+    const int img = b * H * W;                               // B*H*W < 2^31 (checked on the host)
     const float* __restrict__ predb = a.pred + img;
     const float* __restrict__ gtb = a.gt ? a.gt + img : nullptr;
-    const bool has_mask = a.mask != nullptr;
-    const Derived dv = derive(a);
+    const float up = a.upstream;
+
+    // Scalars every pixel needs, derived once per CTA from the phase-A statistics;
+    // weights and the upstream gradient are folded in here so the pixel loop has no extra multiplies.
+    if (tid == 0) {
+        const double n = a.stats[ST_SI_N], S = a.stats[ST_SI_S], nr = a.stats[ST_RP_N];
+        s_c[0] = n > 0.0 ? (float)(2.0 / n) * a.w_si * up : 0.f;                                   // c1
+        s_c[1] = n > 0.0 ? (float)(-2.0 * (double)a.lambda * S / (n * n)) * a.w_si * up : 0.f;     // c2
+        s_c[2] = nr > 0.0 ? (float)(1.0 / nr) * a.w_rp * up : 0.f;                                 // 1/n (reprojection)
+        s_c[3] = SMOOTH ? (1.0f / ((float)(a.img_psum[b] / ((double)H * W)) + a.eps_smooth)) * a.w_smooth * up : 0.f;  // a_b (:192-193)
+    }
 
     float acc[BF_COUNT];
 #pragma unroll
     for (int q = 0; q < BF_COUNT; ++q) acc[q] = 0.f;
 
-    // ---------------- P1: stage raw pred / gt with an 8-pixel halo, edge pixels replicated ----------------
     if constexpr (GRAD) {
-        constexpr int NC4 = FRW / 4;   // 36 float4 per staged row
-        for (int i = tid; i < FRH * NC4; i += kThreadsB) {
-            const int rr = i / NC4, c4 = i - rr * NC4;
-            const int gy = clampi(y0 - HALO + rr, 0, H - 1);
-            const int gx = x0 - HALO + 4 * c4;
-            float4 pv, gv;
-            if (gx >= 0 && gx + 3 < W) {
-                pv = __ldg(reinterpret_cast<const float4*>(predb + (size_t)gy * W + gx));
-                gv = __ldg(reinterpret_cast<const float4*>(gtb + (size_t)gy * W + gx));
-            } else {   // whole float4 outside (W % 4 == 0): replicate the border pixel
-                const int cx = gx < 0 ? 0 : W - 1;
-                const float ps = __ldg(predb + (size_t)gy * W + cx), gs = __ldg(gtb + (size_t)gy * W + cx);
-                pv = make_float4(ps, ps, ps, ps);
-                gv = make_float4(gs, gs, gs, gs);
+        // ---------------- P1: stage raw pred / gt with an 8-pixel halo, edge pixels replicated ----------------
+        for (int rr = warp; rr < FRH; rr += kThreadsB / 32) {
+            const int rowo = clampi(y0 - HALO + rr, 0, H - 1) * W;
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int c4 = pass * 32 + lane;
+                if (c4 < FRW / 4) {
+                    const int gx = x0 - HALO + 4 * c4;
+                    float4 pv, gv;
+                    if (gx >= 0 && gx + 3 < W) {
+                        pv = __ldg(reinterpret_cast<const float4*>(predb + rowo + gx));
+                        gv = __ldg(reinterpret_cast<const float4*>(gtb + rowo + gx));
+                    } else {   // whole float4 outside (W % 4 == 0): replicate the border pixel
+                        const int cx = gx < 0 ? 0 : W - 1;
+                        const float ps = __ldg(predb + rowo + cx), gs = __ldg(gtb + rowo + cx);
+                        pv = make_float4(ps, ps, ps, ps);
+                        gv = make_float4(gs, gs, gs, gs);
+                    }
+                    *reinterpret_cast<float4*>(sm.sp + rr * FRW + 4 * c4) = pv;
+                    *reinterpret_cast<float4*>(sm.sg + rr * FRW + 4 * c4) = gv;
+                }
             }
-            *reinterpret_cast<float4*>(sm.sp + rr * FRW + 4 * c4) = pv;
-            *reinterpret_cast<float4*>(sm.sg + rr * FRW + 4 * c4) = gv;
         }
         __syncthreads();
 
@@ -169,7 +218,7 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
         {
             constexpr int BR = FRH / 8, BC = FRW / 8;   // 8 x 18 blocks of 8x8
             for (int item = tid; item < 2 * BR * BC; item += kThreadsB) {
-                const int t = item / (BR * BC);
+                const int t = item >= BR * BC ? 1 : 0;
                 const int blk = item - t * (BR * BC);
                 const int by = blk / BC, bx = blk - by * BC;
                 const float* src = (t == 0 ? sm.sp : sm.sg) + (by * 8) * FRW + bx * 8;
@@ -189,37 +238,11 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
         }
         __syncthreads();
 
-        // ---------------- P3a: coefficients of scales 3 and 2; P3b: logs in place over the staged tile ----------------
-#pragma unroll
-        for (int s = 3; s >= 2; --s) {
-            int Hs, Ws; float inv_nx, inv_ny;
-            scale_dims(a, s, Hs, Ws, inv_nx, inv_ny);
-            const int ch = FTH >> s, cw = FTW >> s, pw = (FTW >> s) + 2;
-            const float* PL = sm.pl + fpool_off(s);
-            const float* PG = sm.pg + fpool_off(s);
-            float* CC = sm.cc + fcc_off(s);
-            const float spread = 1.0f / (float)((1 << s) * (1 << s)) * 0.25f * a.w_grad;
-            float ax = 0.f, ay = 0.f;
-            for (int i = tid; i < ch * cw; i += kThreadsB) {
-                const int cy = i / cw, cx = i - cy * cw;
-                const int gyc = (y0 >> s) + cy, gxc = (x0 >> s) + cx;
-                float coef = 0.f;
-                if (gyc < Hs && gxc < Ws) {
-                    const int c = (cy + 1) * pw + (cx + 1);
-                    const float lp = PL[c], lg = PG[c];
-                    float sx_r = 0.f, sx_l = 0.f, sy_d = 0.f, sy_u = 0.f;
-                    if (gxc + 1 < Ws) { const float e = (PL[c + 1] - lp) - (PG[c + 1] - lg); ax += fabsf(e); sx_r = sgn3(e); }
-                    if (gxc >= 1) sx_l = sgn3((lp - PL[c - 1]) - (lg - PG[c - 1]));
-                    if (gyc + 1 < Hs) { const float e = (PL[c + pw] - lp) - (PG[c + pw] - lg); ay += fabsf(e); sy_d = sgn3(e); }
-                    if (gyc >= 1) sy_u = sgn3((lp - PL[c - pw]) - (lg - PG[c - pw]));
-                    coef = ((sx_l - sx_r) * inv_nx + (sy_u - sy_d) * inv_ny) * CC[i] * spread;
-                }
-                CC[i] = coef;
-            }
-            acc[BF_GX0 + 2 * s] += ax;
-            acc[BF_GY0 + 2 * s] += ay;
-        }
-        // logs of the (FTH+2) x (FTW+2) ring+interior, in place: 2 pixels per step on the packed pipes
+        // ---------------- P3a: coefficients of scales 3 and 2 ----------------
+        const float wg = 0.25f * a.w_grad * up;              // 1/num_scales * weight * upstream
+        coef_pass<3, false>(a, sm, tid, y0, x0, wg * (1.0f / 64.0f), acc[BF_GX3], acc[BF_GY3]);
+        coef_pass<2, false>(a, sm, tid, y0, x0, wg * (1.0f / 16.0f), acc[BF_GX2], acc[BF_GY2]);
+        // ---------------- P3b: logs of the (FTH+2) x (FTW+2) ring + interior, in place, 2 px per step ----------------
         {
             constexpr int LR = FTH + 2, LC2 = (FTW + 2) / 2;   // 50 rows x 65 pairs
             for (int i = tid; i < LR * LC2; i += kThreadsB) {
@@ -233,42 +256,10 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
             }
         }
         __syncthreads();
-
-        // ---------------- P3c: scale-1 coefficients + the coarser two gathered: what each pixel adds ----------------
-        {
-            constexpr int s = 1;
-            int Hs, Ws; float inv_nx, inv_ny;
-            scale_dims(a, s, Hs, Ws, inv_nx, inv_ny);
-            constexpr int ch = FTH >> 1, cw = FTW >> 1, pw = (FTW >> 1) + 2;
-            const float* PL = sm.pl + fpool_off(1);
-            const float* PG = sm.pg + fpool_off(1);
-            float* CC = sm.cc + fcc_off(1);
-            const float* C2 = sm.cc + fcc_off(2);
-            const float* C3 = sm.cc + fcc_off(3);
-            const float spread = 0.25f * 0.25f * a.w_grad;
-            float ax = 0.f, ay = 0.f;
-            for (int i = tid; i < ch * cw; i += kThreadsB) {
-                const int cy = i / cw, cx = i - cy * cw;
-                const int gyc = (y0 >> 1) + cy, gxc = (x0 >> 1) + cx;
-                float coef = 0.f;
-                if (gyc < Hs && gxc < Ws) {
-                    const int c = (cy + 1) * pw + (cx + 1);
-                    const float lp = PL[c], lg = PG[c];
-                    float sx_r = 0.f, sx_l = 0.f, sy_d = 0.f, sy_u = 0.f;
-                    if (gxc + 1 < Ws) { const float e = (PL[c + 1] - lp) - (PG[c + 1] - lg); ax += fabsf(e); sx_r = sgn3(e); }
-                    if (gxc >= 1) sx_l = sgn3((lp - PL[c - 1]) - (lg - PG[c - 1]));
-                    if (gyc + 1 < Hs) { const float e = (PL[c + pw] - lp) - (PG[c + pw] - lg); ay += fabsf(e); sy_d = sgn3(e); }
-                    if (gyc >= 1) sy_u = sgn3((lp - PL[c - pw]) - (lg - PG[c - pw]));
-                    coef = ((sx_l - sx_r) * inv_nx + (sy_u - sy_d) * inv_ny) * CC[i] * spread;
-                    coef += C2[(cy >> 1) * fcc_w(2) + (cx >> 1)] + C3[(cy >> 2) * fcc_w(3) + (cx >> 2)];
-                }
-                CC[i] = coef;
-            }
-            acc[BF_GX0 + 2] += ax;
-            acc[BF_GY0 + 2] += ay;
-        }
-        __syncthreads();
+        // ---------------- P3c: scale 1 + the two coarser gathered: what each pixel adds ----------------
+        coef_pass<1, true>(a, sm, tid, y0, x0, wg * 0.25f, acc[BF_GX1], acc[BF_GY1]);
     }
+    __syncthreads();
 
     // ---------------- P4: full-resolution pass.  One warp = 128 columns, marching down FRPW rows ----------------
     {
@@ -276,14 +267,15 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
         const int gx0 = x0 + xl;
         const bool lane_in = gx0 < W;                       // W % 4 == 0: a lane is fully inside or outside
         const int r0 = warp * FRPW;
+        const float c1 = s_c[0], c2 = s_c[1], rpn = s_c[2], abw = s_c[3];
 
         // per-column camera geometry (depth_loss.h:290-300)
-        float fxe = 1.f, fye = 1.f, rfx = 1.f, rfy = 1.f, cx = 0.f, cy = 0.f;
+        float fxe = 1.f, fye = 1.f, rfx = 1.f, rfy = 1.f, cyv = 0.f;
         float axk[4] = {0.f, 0.f, 0.f, 0.f}, xhk[4] = {0.f, 0.f, 0.f, 0.f};
         bool mk_ok = true;
         if constexpr (RP) {
-            float fx, fy;
-            load_K(a, b, fx, fy, cx, cy);
+            float fx, fy, cxv;
+            load_K(a, b, fx, fy, cxv, cyv);
             fxe = fx + a.eps_rp;
             fye = fy + a.eps_rp;
             rfx = __frcp_rn(fxe);
@@ -291,217 +283,235 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
             mk_ok = markstein_safe(fxe) && markstein_safe(fye);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                axk[k] = (float)(gx0 + k) - cx;
+                axk[k] = (float)(gx0 + k) - cxv;
                 xhk[k] = __fdiv_rn(axk[k], fxe);
             }
         }
-        float inv_nx0 = 0.f, inv_ny0 = 0.f;
-        if constexpr (GRAD) { int Hs, Ws; scale_dims(a, 0, Hs, Ws, inv_nx0, inv_ny0); }
-        const float g0scale = 0.25f * a.w_grad;             // 1/num_scales * weight
-        float ab_w = 0.f, sm_nx = 0.f, sm_ny = 0.f;
-        if constexpr (SMOOTH) {
-            const float ab = 1.0f / ((float)(a.img_psum[b] / ((double)H * W)) + a.eps_smooth);   // depth_loss.h:192-193
-            ab_w = ab * a.w_smooth;
-            sm_nx = W > 1 ? (float)(1.0 / ((double)a.global_B * H * (W - 1))) : 0.f;
-            sm_ny = H > 1 ? (float)(1.0 / ((double)a.global_B * (H - 1) * W)) : 0.f;
-        }
+        const float inx0 = a.inv_nx[0] * 0.25f * a.w_grad * up, iny0 = a.inv_ny[0] * 0.25f * a.w_grad * up;
+        const float snx = a.sm_nx * abw, sny = a.sm_ny * abw;
+        const float eps_g = a.eps_grad, eps_s = a.eps_si, eps_r = a.eps_rp;
         const float* __restrict__ rgbb = SMOOTH ? a.rgb + (size_t)b * 3 * H * W : nullptr;
-        const size_t plane = (size_t)H * W;
+        const int plane = H * W;
         constexpr float kExpScale = -1.4426950408889634f / 3.0f;    // exp(-mean_c|dI|) = 2^(kExpScale * sum_c|dI|)
+        const int gxr = clampi(gx0 + 4, 0, W - 1);                  // right neighbour column of the last lane
+        const bool right_in = gx0 + 4 < W;
 
-        // ---- row fetch: raw pred (+ right neighbour), gt, rgb (+ right neighbour) of image row gy (clamped) ----
-        struct Row {
-            float p[5];        // own 4 + right neighbour
-            float g[4];
-            float I[3][5];     // own 4 + right neighbour per channel
-        };
-        auto fetch = [&](int gy_raw, Row& R) {
-            const int gy = clampi(gy_raw, 0, H - 1);
+        // ---- row state ----
+        float pc[5], gc[4], Ic[3][5];       // current row: own 4 + right neighbour
+        float pn[5], gn[4], In[3][5];       // next row
+        float lpc[4] = {0.f, 0.f, 0.f, 0.f}, lgc[4] = {0.f, 0.f, 0.f, 0.f};   // logs of the current row
+        float sy_up[4] = {0.f, 0.f, 0.f, 0.f}, ty_up[4] = {0.f, 0.f, 0.f, 0.f};
+
+        auto fetch = [&](int gy_raw, float (&p)[5], float (&g)[4], float (&I)[3][5]) {
+            const bool in_img = (gy_raw >= 0) && (gy_raw < H);
+            const int ro = clampi(gy_raw, 0, H - 1) * W;
             if (lane_in) {
-                const float4 p4 = __ldg(reinterpret_cast<const float4*>(predb + (size_t)gy * W + gx0));
-                R.p[0] = p4.x; R.p[1] = p4.y; R.p[2] = p4.z; R.p[3] = p4.w;
+                const float4 p4 = __ldg(reinterpret_cast<const float4*>(predb + ro + gx0));
+                p[0] = p4.x; p[1] = p4.y; p[2] = p4.z; p[3] = p4.w;
                 if constexpr (SI || RP) {
-                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gtb + (size_t)gy * W + gx0));
-                    R.g[0] = g4.x; R.g[1] = g4.y; R.g[2] = g4.z; R.g[3] = g4.w;
+                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gtb + ro + gx0));
+                    g[0] = g4.x; g[1] = g4.y; g[2] = g4.z; g[3] = g4.w;
                 }
             } else {   // lanes right of the image hold the replicated border pixel (their edges vanish)
-                const float ps = __ldg(predb + (size_t)gy * W + W - 1);
-                R.p[0] = R.p[1] = R.p[2] = R.p[3] = ps;
-                if constexpr (SI || RP) R.g[0] = R.g[1] = R.g[2] = R.g[3] = 0.f;
+                const float ps = __ldg(predb + ro + W - 1);
+                p[0] = p[1] = p[2] = p[3] = ps;
+                if constexpr (SI || RP) g[0] = g[1] = g[2] = g[3] = 0.f;
             }
             if constexpr (SMOOTH) {
-                const bool in_img = (gy_raw >= 0) && (gy_raw < H);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (in_img && lane_in) v = ldg_stream(reinterpret_cast<const float4*>(rgbb + c * plane + (size_t)gy * W + gx0));
-                    R.I[c][0] = v.x; R.I[c][1] = v.y; R.I[c][2] = v.z; R.I[c][3] = v.w;
+                    if (in_img && lane_in) v = ldg_stream(reinterpret_cast<const float4*>(rgbb + c * plane + ro + gx0));
+                    I[c][0] = v.x; I[c][1] = v.y; I[c][2] = v.z; I[c][3] = v.w;
                 }
                 // right neighbours: next lane's first pixel; the last lane reads the (edge-replicated) halo pixel
-                const int gxn = clampi(gx0 + 4, 0, W - 1);
-                float pn = __shfl_down_sync(0xffffffffu, R.p[0], 1);
-                if (lane == 31) pn = __ldg(predb + (size_t)gy * W + gxn);
-                R.p[4] = pn;
+                float pr = __shfl_down_sync(0xffffffffu, p[0], 1);
+                if (lane == 31) pr = __ldg(predb + ro + gxr);
+                p[4] = pr;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    float in = __shfl_down_sync(0xffffffffu, R.I[c][0], 1);
-                    if (lane == 31) in = (in_img && gx0 + 4 < W) ? __ldg(rgbb + c * plane + (size_t)gy * W + gx0 + 4) : 0.f;
-                    R.I[c][4] = in;
+                    float ir = __shfl_down_sync(0xffffffffu, I[c][0], 1);
+                    if (lane == 31) ir = (in_img && right_in) ? __ldg(rgbb + c * plane + ro + gx0 + 4) : 0.f;
+                    I[c][4] = ir;
+                }
+            }
+        };
+        // terms of the vertical edges (row -> row+1): signed gradient-matching residual and smoothness term
+        auto yterms = [&](int r, bool count, float (&sy)[4], float (&ty)[4], float (&lpn)[4], float (&lgn)[4]) {
+            if constexpr (GRAD) {
+                const float4 ad = *reinterpret_cast<const float4*>(sm.sp + (r + 1 + HALO) * FRW + HALO + xl);
+                const float4 bd = *reinterpret_cast<const float4*>(sm.sg + (r + 1 + HALO) * FRW + HALO + xl);
+                lpn[0] = ad.x; lpn[1] = ad.y; lpn[2] = ad.z; lpn[3] = ad.w;
+                lgn[0] = bd.x; lgn[1] = bd.y; lgn[2] = bd.z; lgn[3] = bd.w;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float e = (lpn[k] - lpc[k]) - (lgn[k] - lgc[k]);      // depth_loss.h:151-163
+                    sy[k] = sgn3(e);
+                    if (count) acc[BF_GY0] += fabsf(e);
+                }
+            }
+            if constexpr (SMOOTH) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float s = fabsf(In[0][k] - Ic[0][k]) + fabsf(In[1][k] - Ic[1][k]) + fabsf(In[2][k] - Ic[2][k]);
+                    const float wy = ex2_approx(s * kExpScale);                 // depth_loss.h:218-227
+                    const float d = pn[k] - pc[k];
+                    ty[k] = wy * sgn3(d);
+                    if (count) acc[BF_SMY] = fmaf(wy, fabsf(d), acc[BF_SMY]);
                 }
             }
         };
 
-        // state carried from the row above: signed terms of the edge (y-1 -> y) per column
-        float sy_up[4] = {0.f, 0.f, 0.f, 0.f};     // gradient matching scale 0: sign(e_y)
-        float ty_up[4] = {0.f, 0.f, 0.f, 0.f};     // smoothness: w_y * sign(d_y)
-        Row cur, nxt;
-        fetch(y0 + r0 - 1, cur);
-
-        for (int r = r0 - 1; r < r0 + FRPW; ++r) {
-            const int gy = y0 + r;
-            fetch(gy + 1, nxt);
-            const bool emit = (r >= r0) && (gy < H);         // warp-uniform
-            const bool cnt = emit && lane_in;                // lanes right of the image own no edges
-            float out[4] = {0.f, 0.f, 0.f, 0.f};
-            float sy_dn[4] = {0.f, 0.f, 0.f, 0.f}, ty_dn[4] = {0.f, 0.f, 0.f, 0.f};
-            float lp[4] = {0.f, 0.f, 0.f, 0.f}, lg[4] = {0.f, 0.f, 0.f, 0.f};
-            float smg[4] = {0.f, 0.f, 0.f, 0.f};
-
+        // prologue: the row above this warp's first row only contributes its lower edges
+        fetch(y0 + r0 - 1, pc, gc, Ic);
+        fetch(y0 + r0, pn, gn, In);
+        if constexpr (GRAD) {
+            const float4 a4 = *reinterpret_cast<const float4*>(sm.sp + (r0 - 1 + HALO) * FRW + HALO + xl);
+            const float4 b4 = *reinterpret_cast<const float4*>(sm.sg + (r0 - 1 + HALO) * FRW + HALO + xl);
+            lpc[0] = a4.x; lpc[1] = a4.y; lpc[2] = a4.z; lpc[3] = a4.w;
+            lgc[0] = b4.x; lgc[1] = b4.y; lgc[2] = b4.z; lgc[3] = b4.w;
+        }
+        {
+            float lpn[4], lgn[4];
+            yterms(r0 - 1, false, sy_up, ty_up, lpn, lgn);
             if constexpr (GRAD) {
-                // logs of rows r and r+1 from shared memory (edge-replicated, so border edges vanish)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { lpc[k] = lpn[k]; lgc[k] = lgn[k]; }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) pc[k] = pn[k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gc[k] = gn[k];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) Ic[c][k] = In[c][k];
+
+        for (int r = r0; r < r0 + FRPW; ++r) {
+            const int gy = y0 + r;
+            if (gy >= H) break;                              // warp-uniform
+            fetch(gy + 1, pn, gn, In);
+            float sy_dn[4] = {0.f, 0.f, 0.f, 0.f}, ty_dn[4] = {0.f, 0.f, 0.f, 0.f};
+            float lpn[4] = {0.f, 0.f, 0.f, 0.f}, lgn[4] = {0.f, 0.f, 0.f, 0.f};
+            yterms(r, lane_in, sy_dn, ty_dn, lpn, lgn);
+
+            float gm[4] = {0.f, 0.f, 0.f, 0.f}, smg[4] = {0.f, 0.f, 0.f, 0.f};
+            if constexpr (GRAD) {
                 const float* lprow = sm.sp + (r + HALO) * FRW + HALO + xl;
                 const float* lgrow = sm.sg + (r + HALO) * FRW + HALO + xl;
-                const float4 a4 = *reinterpret_cast<const float4*>(lprow);
-                const float4 b4 = *reinterpret_cast<const float4*>(lgrow);
-                const float4 ad = *reinterpret_cast<const float4*>(lprow + FRW);
-                const float4 bd = *reinterpret_cast<const float4*>(lgrow + FRW);
-                lp[0] = a4.x; lp[1] = a4.y; lp[2] = a4.z; lp[3] = a4.w;
-                lg[0] = b4.x; lg[1] = b4.y; lg[2] = b4.z; lg[3] = b4.w;
-                const float lpd[4] = {ad.x, ad.y, ad.z, ad.w}, lgd[4] = {bd.x, bd.y, bd.z, bd.w};
+                const float lpx[6] = {lprow[-1], lpc[0], lpc[1], lpc[2], lpc[3], lprow[4]};
+                const float lgx[6] = {lgrow[-1], lgc[0], lgc[1], lgc[2], lgc[3], lgrow[4]};
+                float sx[5];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float e = (lpd[k] - lp[k]) - (lgd[k] - lg[k]);          // depth_loss.h:151-163
-                    sy_dn[k] = sgn3(e);
-                    if (cnt) acc[BF_GY0] += fabsf(e);
+                for (int j = 0; j < 5; ++j) {
+                    const float e = (lpx[j + 1] - lpx[j]) - (lgx[j + 1] - lgx[j]);   // depth_loss.h:140-148,162
+                    sx[j] = sgn3(e);
+                    if (j >= 1 && lane_in) acc[BF_GX0] += fabsf(e);                  // the 4 edges this lane owns
                 }
-                if (emit) {
-                    const float lpx[6] = {lprow[-1], lp[0], lp[1], lp[2], lp[3], lprow[4]};
-                    const float lgx[6] = {lgrow[-1], lg[0], lg[1], lg[2], lg[3], lgrow[4]};
-                    float sx[5];
 #pragma unroll
-                    for (int j = 0; j < 5; ++j) sx[j] = sgn3((lpx[j + 1] - lpx[j]) - (lgx[j + 1] - lgx[j]));   // :140-148,162
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (cnt) acc[BF_GX0] += fabsf((lpx[k + 2] - lpx[k + 1]) - (lgx[k + 2] - lgx[k + 1]));
-                        out[k] = ((sx[k] - sx[k + 1]) * inv_nx0 + (sy_up[k] - sy_dn[k]) * inv_ny0) * g0scale;   // x 1/p below
-                    }
-                }
+                for (int k = 0; k < 4; ++k)
+                    gm[k] = (sx[k] - sx[k + 1]) * inx0 + (sy_up[k] - sy_dn[k]) * iny0;   // x 1/p below
             }
-
             if constexpr (SMOOTH) {
+                float tx[5];                                  // tx[j]: edge (x_{j-1} -> x_j); j = 0 belongs to the left lane
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const float s = fabsf(nxt.I[0][k] - cur.I[0][k]) + fabsf(nxt.I[1][k] - cur.I[1][k]) +
-                                    fabsf(nxt.I[2][k] - cur.I[2][k]);
-                    const float wy = ex2_approx(s * kExpScale);                 // depth_loss.h:218-227
-                    const float d = nxt.p[k] - cur.p[k];
-                    ty_dn[k] = wy * sgn3(d);
-                    if (cnt) acc[BF_SMY] += wy * fabsf(d);
+                    const float s = fabsf(Ic[0][k + 1] - Ic[0][k]) + fabsf(Ic[1][k + 1] - Ic[1][k]) + fabsf(Ic[2][k + 1] - Ic[2][k]);
+                    const float wx = ex2_approx(s * kExpScale);                 // depth_loss.h:211-226
+                    const float d = pc[k + 1] - pc[k];
+                    tx[k + 1] = wx * sgn3(d);
+                    if (lane_in) acc[BF_SMX] = fmaf(wx, fabsf(d), acc[BF_SMX]);
                 }
-                if (emit) {
-                    float tx[5];                                                // tx[j]: edge (x_{j-1} -> x_j), j = 0 is the left neighbour's
+                float tl = __shfl_up_sync(0xffffffffu, tx[4], 1);
+                if (lane == 0) {
+                    tl = 0.f;                                 // left neighbour lives in another tile: evaluate that edge here
+                    if (gx0 >= 1) {
+                        const int ro = gy * W;
+                        const float pl_ = __ldg(predb + ro + gx0 - 1);
+                        float s = 0.f;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float s = fabsf(cur.I[0][k + 1] - cur.I[0][k]) + fabsf(cur.I[1][k + 1] - cur.I[1][k]) +
-                                        fabsf(cur.I[2][k + 1] - cur.I[2][k]);
-                        const float wx = ex2_approx(s * kExpScale);             // depth_loss.h:211-226
-                        const float d = cur.p[k + 1] - cur.p[k];
-                        tx[k + 1] = wx * sgn3(d);
-                        if (cnt) acc[BF_SMX] += wx * fabsf(d);
+                        for (int c = 0; c < 3; ++c) s += fabsf(Ic[c][0] - __ldg(rgbb + c * plane + ro + gx0 - 1));
+                        tl = ex2_approx(s * kExpScale) * sgn3(pc[0] - pl_);
                     }
-                    float tl = __shfl_up_sync(0xffffffffu, tx[4], 1);
-                    if (lane == 0) {
-                        // left neighbour lives in another tile: evaluate that one edge here
-                        tl = 0.f;
-                        if (gx0 >= 1) {
-                            const float pl_ = __ldg(predb + (size_t)gy * W + gx0 - 1);
-                            float s = 0.f;
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) s += fabsf(cur.I[c][0] - __ldg(rgbb + c * plane + (size_t)gy * W + gx0 - 1));
-                            tl = ex2_approx(s * kExpScale) * sgn3(cur.p[0] - pl_);
-                        }
-                    }
-                    tx[0] = tl;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)     // d L / d p_j without the mean-normalisation term (added per image later)
-                        smg[k] = ((tx[k] - tx[k + 1]) * sm_nx + (ty_up[k] - ty_dn[k]) * sm_ny) * ab_w;
                 }
+                tx[0] = tl;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)     // d L / d p_j without the mean-normalisation term (added per image later)
+                    smg[k] = (tx[k] - tx[k + 1]) * snx + (ty_up[k] - ty_dn[k]) * sny;
             }
 
-            if (emit) {
-                // pointwise terms + assembly
-                uchar4 mk = make_uchar4(1, 1, 1, 1);
-                if (has_mask && lane_in) mk = __ldg(reinterpret_cast<const uchar4*>(a.mask + img + (size_t)gy * W + gx0));
-                const unsigned char um[4] = {mk.x, mk.y, mk.z, mk.w};
-                float ayv = 0.f, yh = 0.f;
-                if constexpr (RP) {
-                    ayv = (float)gy - cy;
-                    yh = __fdiv_rn(ayv, fye);
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float p = cur.p[k];
-                    const float rp = rcp_approx(p);
-                    float gsum = 0.f;
-                    if constexpr (GRAD) {
-                        const bool cm = (p >= a.eps_grad) && (p <= 1000.0f);      // clamp backward
-                        gsum = cm ? out[k] * rp : 0.f;
-                        gsum += sm.cc[fcc_off(1) + (r >> 1) * fcc_w(1) + ((xl + k) >> 1)];
-                    }
-                    if constexpr (SMOOTH) gsum += smg[k];
-                    if constexpr (SI) {
-                        const float g = cur.g[k];
-                        const bool m = has_mask ? (um[k] != 0) : (g > a.eps_si);
-                        const bool cm = (p >= a.eps_si) && (p <= 1000.0f);
-                        float d;
-                        if constexpr (GRAD) d = lp[k] - lg[k];
-                        else d = log_exact(clamp_nan(p, a.eps_si, 1000.0f)) - log_exact(clamp_nan(g, a.eps_si, 1000.0f));
-                        if (m && cm && dv.si_on) gsum += a.w_si * ((dv.si_c1 * d + dv.si_c2) * rp);
-                    }
-                    if constexpr (RP) {
-                        const float g = cur.g[k];
-                        const bool m = has_mask ? (um[k] != 0) : (g > a.eps_rp);
-                        if (m && dv.rp_on && lane_in) {
-                            // same operations, same order as depth_loss.h:299-315 (see cadl_phase_b.cuh)
-                            float pX, gX, pY, gY;
-                            if (mk_ok) {
-                                pX = div_by_const(__fmul_rn(axk[k], p), fxe, rfx);
-                                gX = div_by_const(__fmul_rn(axk[k], g), fxe, rfx);
-                                pY = div_by_const(__fmul_rn(ayv, p), fye, rfy);
-                                gY = div_by_const(__fmul_rn(ayv, g), fye, rfy);
-                            } else {
-                                pX = __fdiv_rn(__fmul_rn(axk[k], p), fxe);
-                                gX = __fdiv_rn(__fmul_rn(axk[k], g), fxe);
-                                pY = __fdiv_rn(__fmul_rn(ayv, p), fye);
-                                gY = __fdiv_rn(__fmul_rn(ayv, g), fye);
-                            }
-                            const float dX = pX - gX, dY = pY - gY, dZ = p - g;
-                            const float ss = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(dX, dX), __fmul_rn(dY, dY)), __fmul_rn(dZ, dZ)), a.eps_rp);
-                            const float re = rsqrt_approx(ss);
-                            acc[BF_RP_E] += ss * re;                               // e = sqrt(ss)
-                            gsum += a.w_rp * ((dX * xhk[k] + dY * yh + dZ) * re * dv.rp_inv_n);
-                        }
-                    }
-                    out[k] = gsum * a.upstream;
-                }
-                if (a.grad && lane_in)
-                    *reinterpret_cast<float4*>(a.grad + img + (size_t)gy * W + gx0) = make_float4(out[0], out[1], out[2], out[3]);
+            // ---- pointwise terms + assembly ----
+            bool um[4] = {true, true, true, true};
+            if constexpr (HAS_MASK) {
+                uchar4 mk = make_uchar4(0, 0, 0, 0);
+                if (lane_in) mk = __ldg(reinterpret_cast<const uchar4*>(a.mask + img + gy * W + gx0));
+                um[0] = mk.x != 0; um[1] = mk.y != 0; um[2] = mk.z != 0; um[3] = mk.w != 0;
             }
+            float ayv = 0.f, yh = 0.f;
+            if constexpr (RP) {
+                ayv = (float)gy - cyv;
+                yh = __fdiv_rn(ayv, fye);
+            }
+            const float2 ccv = GRAD ? *reinterpret_cast<const float2*>(sm.cc + fcc_off(1) + (r >> 1) * fcc_w(1) + (xl >> 1))
+                                    : make_float2(0.f, 0.f);
+            float out[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float p = pc[k];
+                const float rp = rcp_approx(p);
+                float gsum = smg[k];
+                if constexpr (GRAD) {
+                    const bool cm = in_range_pos(p, eps_g, 1000.0f);            // clamp backward (closed interval)
+                    gsum += (cm ? gm[k] * rp : 0.f) + (k < 2 ? ccv.x : ccv.y);
+                }
+                if constexpr (SI) {
+                    const float g = gc[k];
+                    const bool m = HAS_MASK ? um[k] : (g > eps_s);
+                    const bool cm = in_range_pos(p, eps_s, 1000.0f);
+                    float d;
+                    if constexpr (GRAD) d = lpc[k] - lgc[k];
+                    else d = log_exact(clamp_nan(p, eps_s, 1000.0f)) - log_exact(clamp_nan(g, eps_s, 1000.0f));
+                    if (m && cm) gsum = fmaf(fmaf(c1, d, c2), rp, gsum);
+                }
+                if constexpr (RP) {
+                    const float g = gc[k];
+                    const bool m = HAS_MASK ? um[k] : (g > eps_r);
+                    if (m && lane_in) {
+                        // same operations, same order as depth_loss.h:299-315 (see cadl_phase_b.cuh)
+                        float pX, gX, pY, gY;
+                        if (mk_ok) {
+                            pX = div_by_const(__fmul_rn(axk[k], p), fxe, rfx);
+                            gX = div_by_const(__fmul_rn(axk[k], g), fxe, rfx);
+                            pY = div_by_const(__fmul_rn(ayv, p), fye, rfy);
+                            gY = div_by_const(__fmul_rn(ayv, g), fye, rfy);
+                        } else {
+                            pX = __fdiv_rn(__fmul_rn(axk[k], p), fxe);
+                            gX = __fdiv_rn(__fmul_rn(axk[k], g), fxe);
+                            pY = __fdiv_rn(__fmul_rn(ayv, p), fye);
+                            gY = __fdiv_rn(__fmul_rn(ayv, g), fye);
+                        }
+                        const float dX = pX - gX, dY = pY - gY, dZ = p - g;
+                        const float ss = fmaf(dZ, dZ, fmaf(dY, dY, dX * dX)) + eps_r;
+                        const float re = rsqrt_approx(ss);
+                        acc[BF_RP_E] = fmaf(ss, re, acc[BF_RP_E]);              // e = sqrt(ss)
+                        gsum = fmaf(fmaf(dX, xhk[k], fmaf(dY, yh, dZ)) * re, rpn, gsum);
+                    }
+                }
+                out[k] = gsum;
+            }
+            if (a.grad && lane_in)
+                *reinterpret_cast<float4*>(a.grad + img + gy * W + gx0) = make_float4(out[0], out[1], out[2], out[3]);
 
             // roll the row state
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { sy_up[k] = sy_dn[k]; ty_up[k] = ty_dn[k]; }
-            cur = nxt;
+            for (int k = 0; k < 4; ++k) { sy_up[k] = sy_dn[k]; ty_up[k] = ty_dn[k]; lpc[k] = lpn[k]; lgc[k] = lgn[k]; gc[k] = gn[k]; }
+#pragma unroll
+            for (int k = 0; k < 5; ++k) pc[k] = pn[k];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int k = 0; k < 5; ++k) Ic[c][k] = In[c][k];
         }
     }
 

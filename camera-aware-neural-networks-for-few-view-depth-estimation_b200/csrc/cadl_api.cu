@@ -145,6 +145,13 @@ cudaError_t launch_fast(const PhaseBArgs& a, cudaStream_t st) {
 }
 
 template <int F>
+cudaError_t launch_point_fast(const PhaseBArgs& a, cudaStream_t st) {
+    if (a.mask) phase_b_point_fast_kernel<F, true><<<a.b_rows, kThreadsB, 0, st>>>(a);
+    else phase_b_point_fast_kernel<F, false><<<a.b_rows, kThreadsB, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int F>
 cudaError_t launch_point(const PhaseBArgs& a, cudaStream_t st) {
     phase_b_point_kernel<F><<<a.b_rows, kThreadsB, 0, st>>>(a);
     return cudaGetLastError();
@@ -221,6 +228,16 @@ int run_grad(const float* pred, const float* gt, const float* rgb, const float* 
     cudaError_t e = cudaSuccess;
     if ((t & (CADL_TERM_GRAD | CADL_TERM_SMOOTH)) == 0) {
         a.b_rows = kPointBlocks;
+        const bool pfast = a.vec_ok && p.eps_si > 0.f && p.eps_si <= 1000.f && !g_force_generic;
+        if (pfast) {
+            switch (t) {
+                case CADL_TERM_SI: e = launch_point_fast<FB_SI>(a, st); break;
+                case CADL_TERM_REPROJ: e = launch_point_fast<FB_RP>(a, st); break;
+                case CADL_TERM_SI | CADL_TERM_REPROJ: e = launch_point_fast<FB_SI | FB_RP>(a, st); break;
+                default: return CADL_ERR_UNSUPPORTED;
+            }
+            return cuda_rc(e);
+        }
         switch (t) {
             case CADL_TERM_SI: e = launch_point<FB_SI>(a, st); break;
             case CADL_TERM_REPROJ: e = launch_point<FB_RP>(a, st); break;

@@ -65,9 +65,9 @@ constexpr int HALO = 8;   // 2^(CADL_MAX_SCALES-1)
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 __host__ inline int a_blocks_per_image(int B, int HW) {
-    // 8 resident blocks per SM over 148 SMs in (close to) whole waves, at least 1024 px per block,
-    // each block inside one image
-    int target = (148 * 8) / B;
+    // ~4 resident blocks per SM over 148 SMs in one wave (fat threads amortise the block-end reduction),
+    // at least 1024 px per block, each block inside one image
+    int target = (148 * 4 + B - 1) / B;
     if (target < 1) target = 1;
     int by_size = (HW + 1023) / 1024;
     int n = target < by_size ? target : by_size;

@@ -40,23 +40,23 @@ __device__ __forceinline__ float ratio_for_thresholds(float p, float g, float rp
 }
 
 // Per-thread accumulators of phase A.  Both metric variants take the same per-pixel terms whenever
-// min < gt < max, pred needs no clamping and x + 1e-8f == x (x >= 0.25): those pixels go to ONE set of
-// "common" accumulators; the few others are evaluated separately per variant (slow path).
+// min < gt < max and pred needs no clamping (the trainers' +1e-8 inside the log is applied as an exact
+// first-order correction): those pixels go to ONE set of "common" accumulators.  The few others
+// (gt outside (min,max) but > 0, or pred outside [min,max]) are evaluated separately for the trainer variant
+// and kept in per-thread shared-memory slots so they cost no registers.
 struct AccA {
     float psum, si_s, si_q;
     unsigned si_n, rp_n;
-    float c_absrel, c_sqrel, c_sq, c_logsq;          // common to eval and train
+    float c_absrel, c_sqrel, c_sq, c_logsq;          // eval == train
     unsigned c_n, c_c1, c_c2, c_c3;
     float e_abs, e_l10, e_sump, e_sumg;              // eval-only quantities
-    float eo_absrel, eo_sqrel, eo_sq, eo_logsq;      // eval, slow path
-    unsigned eo_n, eo_c1, eo_c2, eo_c3;
-    float to_absrel, to_sqrel, to_sq, to_logsq;      // train, slow path
-    unsigned to_n, to_c1, to_c2, to_c3;
+    float t_logsq;                                   // train: sum (ld + first-order 1e-8 correction)^2
 };
+constexpr int kToSlots = 8;   // train-only slow path: absrel, sqrel, sq, logsq, n, c1, c2, c3
 
 template <int F, bool HAS_MASK>
-__device__ __forceinline__ void phase_a_px(float p, float g, float psi, float gsi, float lp, float lg, bool um,
-                                           const PhaseAArgs& a, AccA& A) {
+__device__ __forceinline__ void phase_a_px(float p, float g, float lp, float lg, bool um, const PhaseAArgs& a,
+                                           float Lmin, float Lmax, AccA& A, float* s_to) {
     if constexpr (F & FA_PSUM) A.psum += p;                 // depth_loss.h:192 (mean over H,W)
     if constexpr (F & FA_SI) {
         // depth_loss.h:38-47
@@ -74,91 +74,80 @@ __device__ __forceinline__ void phase_a_px(float p, float g, float psi, float gs
     }
     if constexpr ((F & (FA_EV | FA_TR)) != 0) {
         constexpr bool EV = (F & FA_EV) != 0, TR = (F & FA_TR) != 0;
-        const bool fast = a.share_ok && (g > a.g_lo) && (g < a.max_d) && (p >= a.p_lo) && (p <= a.max_d) &&
-                          (HAS_MASK ? um : true);
-        if (fast) {
-            // min < g < max, no clamp, +1e-8 is a no-op: lp, lg are exactly the logs both variants use
-            const float rg = rcp_approx(g), rp = rcp_approx(p);
-            const float diff = p - g, ad = fabsf(diff), sq = diff * diff;          // depth_metrics.h:170-199
-            const float ld = lp - lg;
-            const float ratio = ratio_for_thresholds(p, g, rp, rg);                 // :221
+        // eval terms, pred clamped AFTER masking (depth_metrics.h:154-161, :66); log(pc) without a branch:
+        // inside [min,max] it is the SI log, outside it is one of two constants.
+        const bool ev_ok = (g > a.min_d) && (g < a.max_d) && (HAS_MASK ? um : true);
+        const float pc = clamp_nan(p, a.min_d, a.max_d);
+        const float lpe = (p < a.min_d) ? Lmin : ((p > a.max_d) ? Lmax : lp);
+        const float rg = rcp_approx(g);
+        const float diff = pc - g, ad = fabsf(diff), sq = diff * diff;              // :170-199 (pow(x,2) == x*x)
+        const float ld = lpe - lg;
+        if (ev_ok) {
+            const float ratio = ratio_for_thresholds(pc, g, rcp_approx(pc), rg);    // :221
             A.c_absrel = fmaf(ad, rg, A.c_absrel);
             A.c_sqrel = fmaf(sq, rg, A.c_sqrel);
             A.c_sq += sq;
             A.c_logsq = fmaf(ld, ld, A.c_logsq);
             A.c_n += 1u;
-            A.c_c1 += (ratio < 1.25f) ? 1u : 0u;                                    // :224-229, trainer :434-436
+            A.c_c1 += (ratio < 1.25f) ? 1u : 0u;                                    // :224-229
             A.c_c2 += (ratio < 1.5625f) ? 1u : 0u;
             A.c_c3 += (ratio < 1.953125f) ? 1u : 0u;
             if constexpr (EV) {
                 A.e_abs += ad;
                 A.e_l10 += fabsf(ld);                                               // x log10(e) at the end (:206)
-                A.e_sump += p;
-                A.e_sumg += g;
-            }
-        } else {
-            const bool ev_ok = EV && (g > a.min_d) && (g < a.max_d) && (HAS_MASK ? um : true);   // :154-161
-            const bool tr_ok = TR && (g > 0.0f);                                                  // trainer :410
-            if (ev_ok) {
-                const float pc = clamp_nan(p, a.min_d, a.max_d);                    // :66
-                const float diff = pc - g, ad = fabsf(diff), sq = diff * diff;
-                const float ld = logf(pc) - logf(g);
-                const float ratio = fmaxf(__fdiv_rn(pc, g), __fdiv_rn(g, pc));
-                const float rg = rcp_approx(g);
-                A.eo_absrel = fmaf(ad, rg, A.eo_absrel);
-                A.eo_sqrel = fmaf(sq, rg, A.eo_sqrel);
-                A.eo_sq += sq;
-                A.eo_logsq = fmaf(ld, ld, A.eo_logsq);
-                A.eo_n += 1u;
-                A.eo_c1 += (ratio < 1.25f) ? 1u : 0u;
-                A.eo_c2 += (ratio < 1.25f * 1.25f) ? 1u : 0u;
-                A.eo_c3 += (ratio < 1.25f * 1.25f * 1.25f) ? 1u : 0u;
-                A.e_abs += ad;
-                A.e_l10 += fabsf(ld);
                 A.e_sump += pc;
                 A.e_sumg += g;
             }
-            if (tr_ok) {
-                // trainer :419-436: no clamp, log(x + 1e-8)
-                const float adt = fabsf(p - g), sqt = adt * adt;
+            if constexpr (TR) {
+                if (pc == p) {
+                    // trainer :429: log(x + 1e-8).  (x + 1e-8f) - x is exact, so log(x + dx) = log x + dx/x to
+                    // well below one ulp; dx is 0 for x >= 0.25.
+                    const float dp = (p + 1e-8f) - p, dg = (g + 1e-8f) - g;
+                    const float ldt = ld + fmaf(dp, rcp_approx(p), -dg * rg);
+                    A.t_logsq = fmaf(ldt, ldt, A.t_logsq);
+                }
+            }
+        }
+        if constexpr (TR) {
+            // trainer-only pixels: gt > 0 outside (min,max), or pred clamped by the eval variant
+            const bool slow = (g > 0.0f) && (!ev_ok || !(pc == p));                  // trainer :410
+            if (slow) {
+                const float adt = fabsf(p - g), sqt = adt * adt;                     // :419-436, no clamp
                 const float ldt = logf(p + 1e-8f) - logf(g + 1e-8f);
                 const float rt = fmaxf(__fdiv_rn(p, g), __fdiv_rn(g, p));
-                const float rg = rcp_approx(g);
-                A.to_absrel = fmaf(adt, rg, A.to_absrel);
-                A.to_sqrel = fmaf(sqt, rg, A.to_sqrel);
-                A.to_sq += sqt;
-                A.to_logsq = fmaf(ldt, ldt, A.to_logsq);
-                A.to_n += 1u;
-                A.to_c1 += (rt < 1.25f) ? 1u : 0u;
-                A.to_c2 += (rt < 1.5625f) ? 1u : 0u;
-                A.to_c3 += (rt < 1.953125f) ? 1u : 0u;
+                const int t = threadIdx.x;
+                // "to" = train-only additions; where the pixel was also counted as common (ev_ok, clamped
+                // pred) the common contribution is taken back out so train = common + to stays exact in form
+                const float sgn = ev_ok ? 1.f : 0.f;
+                s_to[0 * kThreadsA + t] += adt * rg - sgn * ad * rg;
+                s_to[1 * kThreadsA + t] += sqt * rg - sgn * sq * rg;
+                s_to[2 * kThreadsA + t] += sqt - sgn * sq;
+                s_to[3 * kThreadsA + t] += ldt * ldt;
+                const float rc = ev_ok ? fmaxf(__fdiv_rn(pc, g), __fdiv_rn(g, pc)) : 3.0f;
+                s_to[4 * kThreadsA + t] += 1.f - sgn;
+                s_to[5 * kThreadsA + t] += ((rt < 1.25f) ? 1.f : 0.f) - sgn * ((rc < 1.25f) ? 1.f : 0.f);
+                s_to[6 * kThreadsA + t] += ((rt < 1.5625f) ? 1.f : 0.f) - sgn * ((rc < 1.5625f) ? 1.f : 0.f);
+                s_to[7 * kThreadsA + t] += ((rt < 1.953125f) ? 1.f : 0.f) - sgn * ((rc < 1.953125f) ? 1.f : 0.f);
             }
         }
     }
-    (void)psi; (void)gsi;
 }
 
 template <int F, bool HAS_MASK>
 __device__ __forceinline__ void phase_a_quad(const float (&p)[4], const float (&g)[4], const bool (&um)[4],
-                                             const PhaseAArgs& a, AccA& A) {
+                                             const PhaseAArgs& a, float Lmin, float Lmax, AccA& A, float* s_to) {
     float lp[4] = {0.f, 0.f, 0.f, 0.f}, lg[4] = {0.f, 0.f, 0.f, 0.f};
-    float psi[4] = {0.f, 0.f, 0.f, 0.f}, gsi[4] = {0.f, 0.f, 0.f, 0.f};
     if constexpr ((F & (FA_SI | FA_EV | FA_TR)) != 0) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            psi[k] = clamp_nan(p[k], a.eps_si, 1000.0f);     // depth_loss.h:43-44
-            gsi[k] = clamp_nan(g[k], a.eps_si, 1000.0f);
-        }
-#pragma unroll
         for (int k = 0; k < 4; k += 2) {
-            const float2 a2 = log_exact2(make_float2(psi[k], psi[k + 1]));
-            const float2 b2 = log_exact2(make_float2(gsi[k], gsi[k + 1]));
-            lp[k] = a2.x; lp[k + 1] = a2.y;
+            const float2 a2 = log_exact2(make_float2(clamp_nan(p[k], a.eps_si, 1000.0f), clamp_nan(p[k + 1], a.eps_si, 1000.0f)));
+            const float2 b2 = log_exact2(make_float2(clamp_nan(g[k], a.eps_si, 1000.0f), clamp_nan(g[k + 1], a.eps_si, 1000.0f)));
+            lp[k] = a2.x; lp[k + 1] = a2.y;                  // depth_loss.h:43-47
             lg[k] = b2.x; lg[k + 1] = b2.y;
         }
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) phase_a_px<F, HAS_MASK>(p[k], g[k], psi[k], gsi[k], lp[k], lg[k], um[k], a, A);
+    for (int k = 0; k < 4; ++k) phase_a_px<F, HAS_MASK>(p[k], g[k], lp[k], lg[k], um[k], a, Lmin, Lmax, A, s_to);
 }
 
 // Deterministic block-wide sum of one double per thread (fixed shuffle/tree order).
@@ -177,13 +166,14 @@ __device__ __forceinline__ double block_sum_double(double v, double* scratch /*>
 }
 
 template <int F, bool HAS_MASK>
-__global__ void __launch_bounds__(kThreadsA) phase_a_kernel(const PhaseAArgs a) {
+__global__ void __launch_bounds__(kThreadsA, 4) phase_a_kernel(const PhaseAArgs a) {
     constexpr bool NEED_P = (F & (FA_SI | FA_PSUM | FA_EV | FA_TR)) != 0;
     constexpr bool NEED_G = (F & (FA_SI | FA_RP | FA_EV | FA_TR)) != 0;
     __shared__ float s_f[kThreadsA / 32][AF_COUNT];
-    __shared__ unsigned s_i[AI_COUNT];
     __shared__ double s_d[8];
     __shared__ int s_last;
+    __shared__ float s_to[kToSlots * kThreadsA];
+    __shared__ unsigned s_iw[kThreadsA / 32][AI_COUNT];
 
     const int b = blockIdx.y, k = blockIdx.x;
     const int tid = threadIdx.x;
@@ -192,7 +182,10 @@ __global__ void __launch_bounds__(kThreadsA) phase_a_kernel(const PhaseAArgs a) 
 
     AccA A;
     memset(&A, 0, sizeof(A));
-    if (tid < AI_COUNT) s_i[tid] = 0u;
+#pragma unroll
+    for (int q = 0; q < kToSlots; ++q) s_to[q * kThreadsA + tid] = 0.f;   // private slots: no sync needed
+    // log(min_depth), log(max_depth): what log(clamp(pred)) is outside [min,max]
+    const float Lmin = (F & (FA_EV | FA_TR)) ? logf(a.min_d) : 0.f, Lmax = (F & (FA_EV | FA_TR)) ? logf(a.max_d) : 0.f;
 
     if (a.vec_ok) {
         const int nvec = a.HW >> 2;
@@ -212,12 +205,12 @@ __global__ void __launch_bounds__(kThreadsA) phase_a_kernel(const PhaseAArgs a) 
             {
                 const float pp[4] = {p0.x, p0.y, p0.z, p0.w}, gg[4] = {g0.x, g0.y, g0.z, g0.w};
                 const bool mm[4] = {u0.x != 0, u0.y != 0, u0.z != 0, u0.w != 0};
-                phase_a_quad<F, HAS_MASK>(pp, gg, mm, a, A);
+                phase_a_quad<F, HAS_MASK>(pp, gg, mm, a, Lmin, Lmax, A, s_to);
             }
             if (hj) {
                 const float pp[4] = {p1.x, p1.y, p1.z, p1.w}, gg[4] = {g1.x, g1.y, g1.z, g1.w};
                 const bool mm[4] = {u1.x != 0, u1.y != 0, u1.z != 0, u1.w != 0};
-                phase_a_quad<F, HAS_MASK>(pp, gg, mm, a, A);
+                phase_a_quad<F, HAS_MASK>(pp, gg, mm, a, Lmin, Lmax, A, s_to);
             }
         }
     } else {
@@ -227,33 +220,36 @@ __global__ void __launch_bounds__(kThreadsA) phase_a_kernel(const PhaseAArgs a) 
             float p = NEED_P ? __ldg(a.pred + base + i) : 0.f;
             float g = NEED_G ? __ldg(a.gt + base + i) : 0.f;
             bool um = has_mask ? (__ldg(a.mask + base + i) != 0) : true;
-            float lp = 0.f, lg = 0.f, psi = 0.f, gsi = 0.f;
+            float lp = 0.f, lg = 0.f;
             if constexpr ((F & (FA_SI | FA_EV | FA_TR)) != 0) {
-                psi = clamp_nan(p, a.eps_si, 1000.0f);
-                gsi = clamp_nan(g, a.eps_si, 1000.0f);
-                lp = log_exact(psi);
-                lg = log_exact(gsi);
+                lp = log_exact(clamp_nan(p, a.eps_si, 1000.0f));
+                lg = log_exact(clamp_nan(g, a.eps_si, 1000.0f));
             }
-            phase_a_px<F, HAS_MASK>(p, g, psi, gsi, lp, lg, um, a, A);
+            phase_a_px<F, HAS_MASK>(p, g, lp, lg, um, a, Lmin, Lmax, A, s_to);
         }
     }
 
-    // ---- fold the common / slow-path accumulators into the per-variant sums ----
+    // ---- fold the common / train-only accumulators into the per-variant sums ----
     float af[AF_COUNT];
     unsigned ai[AI_COUNT];
+    constexpr bool EVc = (F & FA_EV) != 0, TRc = (F & FA_TR) != 0;
     af[AF_SI_S] = A.si_s; af[AF_SI_Q] = A.si_q; af[AF_PSUM] = A.psum;
-    af[AF_EV_ABSREL] = A.c_absrel + A.eo_absrel; af[AF_EV_SQREL] = A.c_sqrel + A.eo_sqrel;
-    af[AF_EV_SQ] = A.c_sq + A.eo_sq; af[AF_EV_LOGSQ] = A.c_logsq + A.eo_logsq;
+    af[AF_EV_ABSREL] = EVc ? A.c_absrel : 0.f; af[AF_EV_SQREL] = EVc ? A.c_sqrel : 0.f;
+    af[AF_EV_SQ] = EVc ? A.c_sq : 0.f; af[AF_EV_LOGSQ] = EVc ? A.c_logsq : 0.f;
     af[AF_EV_ABS] = A.e_abs; af[AF_EV_LOG10] = A.e_l10 * 0.43429448190325182765f;   // log10 x = ln x / ln 10
     af[AF_EV_SUMP] = A.e_sump; af[AF_EV_SUMG] = A.e_sumg;
-    af[AF_TR_ABSREL] = A.c_absrel + A.to_absrel; af[AF_TR_SQREL] = A.c_sqrel + A.to_sqrel;
-    af[AF_TR_SQ] = A.c_sq + A.to_sq; af[AF_TR_LOGSQ] = A.c_logsq + A.to_logsq;
+    af[AF_TR_ABSREL] = TRc ? A.c_absrel + s_to[0 * kThreadsA + tid] : 0.f;
+    af[AF_TR_SQREL] = TRc ? A.c_sqrel + s_to[1 * kThreadsA + tid] : 0.f;
+    af[AF_TR_SQ] = TRc ? A.c_sq + s_to[2 * kThreadsA + tid] : 0.f;
+    af[AF_TR_LOGSQ] = TRc ? A.t_logsq + s_to[3 * kThreadsA + tid] : 0.f;
     ai[AI_SI_N] = A.si_n; ai[AI_RP_N] = A.rp_n;
-    constexpr unsigned ev = (F & FA_EV) ? 1u : 0u, tr = (F & FA_TR) ? 1u : 0u;
-    ai[AI_EV_N] = ev * A.c_n + A.eo_n; ai[AI_EV_C1] = ev * A.c_c1 + A.eo_c1;
-    ai[AI_EV_C2] = ev * A.c_c2 + A.eo_c2; ai[AI_EV_C3] = ev * A.c_c3 + A.eo_c3;
-    ai[AI_TR_N] = tr * A.c_n + A.to_n; ai[AI_TR_C1] = tr * A.c_c1 + A.to_c1;
-    ai[AI_TR_C2] = tr * A.c_c2 + A.to_c2; ai[AI_TR_C3] = tr * A.c_c3 + A.to_c3;
+    ai[AI_EV_N] = EVc ? A.c_n : 0u; ai[AI_EV_C1] = EVc ? A.c_c1 : 0u;
+    ai[AI_EV_C2] = EVc ? A.c_c2 : 0u; ai[AI_EV_C3] = EVc ? A.c_c3 : 0u;
+    // the train-only slots hold small signed integers as floats (exact)
+    ai[AI_TR_N] = TRc ? (unsigned)((int)A.c_n + (int)s_to[4 * kThreadsA + tid]) : 0u;
+    ai[AI_TR_C1] = TRc ? (unsigned)((int)A.c_c1 + (int)s_to[5 * kThreadsA + tid]) : 0u;
+    ai[AI_TR_C2] = TRc ? (unsigned)((int)A.c_c2 + (int)s_to[6 * kThreadsA + tid]) : 0u;
+    ai[AI_TR_C3] = TRc ? (unsigned)((int)A.c_c3 + (int)s_to[7 * kThreadsA + tid]) : 0u;
 
     // ---- block reduction: fp32 warp shuffle, then fp64 across warps in warp order ----
     const int warp = tid >> 5, lane = tid & 31;
@@ -266,7 +262,7 @@ __global__ void __launch_bounds__(kThreadsA) phase_a_kernel(const PhaseAArgs a) 
 #pragma unroll
     for (int q = 0; q < AI_COUNT; ++q) {
         unsigned v = warp_sum(ai[q]);
-        if (lane == 0 && v) atomicAdd(&s_i[q], v);
+        if (lane == 0) s_iw[warp][q] = v;
     }
     const int blk = b * a.blocks_per_img + k;
     if (tid < AF_COUNT) {
@@ -276,7 +272,12 @@ __global__ void __launch_bounds__(kThreadsA) phase_a_kernel(const PhaseAArgs a) 
         a.a_part[(size_t)blk * AF_COUNT + tid] = acc;
     }
     __syncthreads();
-    if (tid < AI_COUNT && s_i[tid]) atomicAdd(&a.hdr->icount[tid], (unsigned long long)s_i[tid]);
+    if (tid < AI_COUNT) {
+        unsigned t = 0;
+#pragma unroll
+        for (int w = 0; w < kThreadsA / 32; ++w) t += s_iw[w][tid];
+        if (t) atomicAdd(&a.hdr->icount[tid], (unsigned long long)t);
+    }
 
     // ---- ticket: the last block to arrive reduces all partial rows in a fixed order ----
     __threadfence();

@@ -297,25 +297,22 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
         const bool right_in = gx0 + 4 < W;
 
         // ---- row state ----
-        float pc[5], gc[4], Ic[3][5];       // current row: own 4 + right neighbour
-        float pn[5], gn[4], In[3][5];       // next row
+        float pc[5], Ic[3][5];              // current row: own 4 + right neighbour
+        float pn[5], In[3][5];              // next row (index 4 filled by finish_row once the loads have landed)
+        float hn_p = 0.f, hn_I[3] = {0.f, 0.f, 0.f};   // last lane's halo pixel of the next row
         float lpc[4] = {0.f, 0.f, 0.f, 0.f}, lgc[4] = {0.f, 0.f, 0.f, 0.f};   // logs of the current row
         float sy_up[4] = {0.f, 0.f, 0.f, 0.f}, ty_up[4] = {0.f, 0.f, 0.f, 0.f};
 
-        auto fetch = [&](int gy_raw, float (&p)[5], float (&g)[4], float (&I)[3][5]) {
+        // issue the global loads of one image row (clamped at the borders); no use of the values here
+        auto fetch = [&](int gy_raw, float (&p)[5], float (&I)[3][5], float& hp, float (&hI)[3]) {
             const bool in_img = (gy_raw >= 0) && (gy_raw < H);
             const int ro = clampi(gy_raw, 0, H - 1) * W;
             if (lane_in) {
                 const float4 p4 = __ldg(reinterpret_cast<const float4*>(predb + ro + gx0));
                 p[0] = p4.x; p[1] = p4.y; p[2] = p4.z; p[3] = p4.w;
-                if constexpr (SI || RP) {
-                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gtb + ro + gx0));
-                    g[0] = g4.x; g[1] = g4.y; g[2] = g4.z; g[3] = g4.w;
-                }
             } else {   // lanes right of the image hold the replicated border pixel (their edges vanish)
                 const float ps = __ldg(predb + ro + W - 1);
                 p[0] = p[1] = p[2] = p[3] = ps;
-                if constexpr (SI || RP) g[0] = g[1] = g[2] = g[3] = 0.f;
             }
             if constexpr (SMOOTH) {
 #pragma unroll
@@ -324,15 +321,22 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
                     if (in_img && lane_in) v = ldg_stream(reinterpret_cast<const float4*>(rgbb + c * plane + ro + gx0));
                     I[c][0] = v.x; I[c][1] = v.y; I[c][2] = v.z; I[c][3] = v.w;
                 }
-                // right neighbours: next lane's first pixel; the last lane reads the (edge-replicated) halo pixel
-                float pr = __shfl_down_sync(0xffffffffu, p[0], 1);
-                if (lane == 31) pr = __ldg(predb + ro + gxr);
-                p[4] = pr;
+                if (lane == 31) {   // the right neighbour of the last lane lives in the next tile (or is replicated)
+                    hp = __ldg(predb + ro + gxr);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) hI[c] = (in_img && right_in) ? __ldg(rgbb + c * plane + ro + gx0 + 4) : 0.f;
+                }
+            }
+        };
+        // right neighbours across lanes -- called when the row becomes current, long after its loads were issued
+        auto finish_row = [&](float (&p)[5], float (&I)[3][5], float hp, const float (&hI)[3]) {
+            if constexpr (SMOOTH) {
+                const float pr = __shfl_down_sync(0xffffffffu, p[0], 1);
+                p[4] = (lane == 31) ? hp : pr;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    float ir = __shfl_down_sync(0xffffffffu, I[c][0], 1);
-                    if (lane == 31) ir = (in_img && right_in) ? __ldg(rgbb + c * plane + ro + gx0 + 4) : 0.f;
-                    I[c][4] = ir;
+                    const float ir = __shfl_down_sync(0xffffffffu, I[c][0], 1);
+                    I[c][4] = (lane == 31) ? hI[c] : ir;
                 }
             }
         };
@@ -363,8 +367,11 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
         };
 
         // prologue: the row above this warp's first row only contributes its lower edges
-        fetch(y0 + r0 - 1, pc, gc, Ic);
-        fetch(y0 + r0, pn, gn, In);
+        {
+            float hp0 = 0.f, hI0[3] = {0.f, 0.f, 0.f};
+            fetch(y0 + r0 - 1, pc, Ic, hp0, hI0);
+            fetch(y0 + r0, pn, In, hn_p, hn_I);
+        }
         if constexpr (GRAD) {
             const float4 a4 = *reinterpret_cast<const float4*>(sm.sp + (r0 - 1 + HALO) * FRW + HALO + xl);
             const float4 b4 = *reinterpret_cast<const float4*>(sm.sg + (r0 - 1 + HALO) * FRW + HALO + xl);
@@ -379,10 +386,9 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
                 for (int k = 0; k < 4; ++k) { lpc[k] = lpn[k]; lgc[k] = lgn[k]; }
             }
         }
+        finish_row(pn, In, hn_p, hn_I);
 #pragma unroll
         for (int k = 0; k < 5; ++k) pc[k] = pn[k];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) gc[k] = gn[k];
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -391,11 +397,18 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
         for (int r = r0; r < r0 + FRPW; ++r) {
             const int gy = y0 + r;
             if (gy >= H) break;                              // warp-uniform
-            fetch(gy + 1, pn, gn, In);
-            float sy_dn[4] = {0.f, 0.f, 0.f, 0.f}, ty_dn[4] = {0.f, 0.f, 0.f, 0.f};
-            float lpn[4] = {0.f, 0.f, 0.f, 0.f}, lgn[4] = {0.f, 0.f, 0.f, 0.f};
-            yterms(r, lane_in, sy_dn, ty_dn, lpn, lgn);
+            // 1. issue next row's loads; they are consumed at step 4, after ~2/3 of this row's arithmetic
+            fetch(gy + 1, pn, In, hn_p, hn_I);
+            float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (SI || RP) {
+                if (lane_in) g4 = __ldg(reinterpret_cast<const float4*>(gtb + gy * W + gx0));
+            }
+            uchar4 mk4 = make_uchar4(0, 0, 0, 0);
+            if constexpr (HAS_MASK) {
+                if (lane_in) mk4 = __ldg(reinterpret_cast<const uchar4*>(a.mask + img + gy * W + gx0));
+            }
 
+            // 2. horizontal edges of the current row
             float gm[4] = {0.f, 0.f, 0.f, 0.f}, smg[4] = {0.f, 0.f, 0.f, 0.f};
             if constexpr (GRAD) {
                 const float* lprow = sm.sp + (r + HALO) * FRW + HALO + xl;
@@ -410,8 +423,7 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
                     if (j >= 1 && lane_in) acc[BF_GX0] += fabsf(e);                  // the 4 edges this lane owns
                 }
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    gm[k] = (sx[k] - sx[k + 1]) * inx0 + (sy_up[k] - sy_dn[k]) * iny0;   // x 1/p below
+                for (int k = 0; k < 4; ++k) gm[k] = (sx[k] - sx[k + 1]) * inx0;
             }
             if constexpr (SMOOTH) {
                 float tx[5];                                  // tx[j]: edge (x_{j-1} -> x_j); j = 0 belongs to the left lane
@@ -437,45 +449,35 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
                 }
                 tx[0] = tl;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)     // d L / d p_j without the mean-normalisation term (added per image later)
-                    smg[k] = (tx[k] - tx[k + 1]) * snx + (ty_up[k] - ty_dn[k]) * sny;
+                for (int k = 0; k < 4; ++k) smg[k] = (tx[k] - tx[k + 1]) * snx;
             }
 
-            // ---- pointwise terms + assembly ----
-            bool um[4] = {true, true, true, true};
-            if constexpr (HAS_MASK) {
-                uchar4 mk = make_uchar4(0, 0, 0, 0);
-                if (lane_in) mk = __ldg(reinterpret_cast<const uchar4*>(a.mask + img + gy * W + gx0));
-                um[0] = mk.x != 0; um[1] = mk.y != 0; um[2] = mk.z != 0; um[3] = mk.w != 0;
-            }
+            // 3. pointwise terms
+            const float gcur[4] = {g4.x, g4.y, g4.z, g4.w};
+            const bool um[4] = {mk4.x != 0, mk4.y != 0, mk4.z != 0, mk4.w != 0};
             float ayv = 0.f, yh = 0.f;
             if constexpr (RP) {
                 ayv = (float)gy - cyv;
-                yh = __fdiv_rn(ayv, fye);
+                yh = ayv * rfy;                               // d pY / d p (tolerance path)
             }
             const float2 ccv = GRAD ? *reinterpret_cast<const float2*>(sm.cc + fcc_off(1) + (r >> 1) * fcc_w(1) + (xl >> 1))
                                     : make_float2(0.f, 0.f);
-            float out[4];
+            float rpk[4], pw[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float p = pc[k];
-                const float rp = rcp_approx(p);
-                float gsum = smg[k];
-                if constexpr (GRAD) {
-                    const bool cm = in_range_pos(p, eps_g, 1000.0f);            // clamp backward (closed interval)
-                    gsum += (cm ? gm[k] * rp : 0.f) + (k < 2 ? ccv.x : ccv.y);
-                }
+                rpk[k] = rcp_approx(p);
+                float gsum = (k < 2 ? ccv.x : ccv.y);
                 if constexpr (SI) {
-                    const float g = gc[k];
+                    const float g = gcur[k];
                     const bool m = HAS_MASK ? um[k] : (g > eps_s);
-                    const bool cm = in_range_pos(p, eps_s, 1000.0f);
                     float d;
                     if constexpr (GRAD) d = lpc[k] - lgc[k];
                     else d = log_exact(clamp_nan(p, eps_s, 1000.0f)) - log_exact(clamp_nan(g, eps_s, 1000.0f));
-                    if (m && cm) gsum = fmaf(fmaf(c1, d, c2), rp, gsum);
+                    if (m && in_range_pos(p, eps_s, 1000.0f)) gsum = fmaf(fmaf(c1, d, c2), rpk[k], gsum);
                 }
                 if constexpr (RP) {
-                    const float g = gc[k];
+                    const float g = gcur[k];
                     const bool m = HAS_MASK ? um[k] : (g > eps_r);
                     if (m && lane_in) {
                         // same operations, same order as depth_loss.h:299-315 (see cadl_phase_b.cuh)
@@ -498,14 +500,31 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
                         gsum = fmaf(fmaf(dX, xhk[k], fmaf(dY, yh, dZ)) * re, rpn, gsum);
                     }
                 }
+                pw[k] = gsum;
+            }
+
+            // 4. vertical edges (needs the next row), then assembly and the 128-bit store
+            float sy_dn[4] = {0.f, 0.f, 0.f, 0.f}, ty_dn[4] = {0.f, 0.f, 0.f, 0.f};
+            float lpn[4] = {0.f, 0.f, 0.f, 0.f}, lgn[4] = {0.f, 0.f, 0.f, 0.f};
+            yterms(r, lane_in, sy_dn, ty_dn, lpn, lgn);
+            float out[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float gsum = pw[k];
+                if constexpr (SMOOTH) gsum += fmaf(ty_up[k] - ty_dn[k], sny, smg[k]);
+                if constexpr (GRAD) {
+                    const float gmk = fmaf(sy_up[k] - sy_dn[k], iny0, gm[k]);
+                    gsum = in_range_pos(pc[k], eps_g, 1000.0f) ? fmaf(gmk, rpk[k], gsum) : gsum;   // clamp backward
+                }
                 out[k] = gsum;
             }
             if (a.grad && lane_in)
                 *reinterpret_cast<float4*>(a.grad + img + gy * W + gx0) = make_float4(out[0], out[1], out[2], out[3]);
 
             // roll the row state
+            finish_row(pn, In, hn_p, hn_I);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { sy_up[k] = sy_dn[k]; ty_up[k] = ty_dn[k]; lpc[k] = lpn[k]; lgc[k] = lgn[k]; gc[k] = gn[k]; }
+            for (int k = 0; k < 4; ++k) { sy_up[k] = sy_dn[k]; ty_up[k] = ty_dn[k]; lpc[k] = lpn[k]; lgc[k] = lgn[k]; }
 #pragma unroll
             for (int k = 0; k < 5; ++k) pc[k] = pn[k];
 #pragma unroll
@@ -516,6 +535,119 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
     }
 
     if (publish_partials(a, acc, tile, s_f, &s_last)) {
+        finalize_results(a, s_d);
+        if (tid == 0 && a.metrics) write_metric_results(a.stats, a.metrics, *a.results);
+    }
+}
+
+
+// ================================================================================================
+// Fast streaming kernel for the pointwise terms alone (BASELINE config 2: reprojection fwd+bwd).
+// One warp per 128-pixel row segment, 2 segments in flight per warp; 12 B/px of HBM traffic.
+// Requires W % 4 == 0 and 16-byte aligned tensors (same dispatch condition as the tile fast path).
+// ================================================================================================
+template <int F, bool HAS_MASK>
+__global__ void __launch_bounds__(kThreadsB) phase_b_point_fast_kernel(const PhaseBArgs a) {
+    __shared__ float s_f[kThreadsB / 32][BF_COUNT];
+    __shared__ double s_d[8];
+    __shared__ float s_c[4];
+    __shared__ int s_last;
+    constexpr bool SI = (F & FB_SI) != 0, RP = (F & FB_RP) != 0;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float up = a.upstream;
+    if (tid == 0) {
+        const double n = a.stats[ST_SI_N], S = a.stats[ST_SI_S], nr = a.stats[ST_RP_N];
+        s_c[0] = n > 0.0 ? (float)(2.0 / n) * a.w_si * up : 0.f;
+        s_c[1] = n > 0.0 ? (float)(-2.0 * (double)a.lambda * S / (n * n)) * a.w_si * up : 0.f;
+        s_c[2] = nr > 0.0 ? (float)(1.0 / nr) * a.w_rp * up : 0.f;
+    }
+    __syncthreads();
+    const float c1 = s_c[0], c2 = s_c[1], rpn = s_c[2];
+    const float eps_s = a.eps_si, eps_r = a.eps_rp;
+    float acc[BF_COUNT];
+#pragma unroll
+    for (int q = 0; q < BF_COUNT; ++q) acc[q] = 0.f;
+
+    const int H = a.H, W = a.W;
+    const int segs = (W + 127) >> 7;
+    const int items = a.B * H * segs;                    // < 2^31 (host-checked)
+    const int wstride = gridDim.x * (kThreadsB / 32);
+    int cached_b = -1;
+    float fxe = 1.f, fye = 1.f, rfx = 1.f, rfy = 1.f, cxv = 0.f, cyv = 0.f;
+    bool mk_ok = true;
+    for (int it = blockIdx.x * (kThreadsB / 32) + warp; it < items; it += wstride) {
+        const int row = it / segs, seg = it - row * segs;
+        const int b = row / H, y = row - b * H;
+        const int x = (seg << 7) + 4 * lane;
+        if (x >= W) continue;
+        const int off = row * W + x;
+        const float4 p4 = __ldg(reinterpret_cast<const float4*>(a.pred + off));
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.gt + off));
+        bool um[4] = {true, true, true, true};
+        if constexpr (HAS_MASK) {
+            const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(a.mask + off));
+            um[0] = u.x != 0; um[1] = u.y != 0; um[2] = u.z != 0; um[3] = u.w != 0;
+        }
+        const float p[4] = {p4.x, p4.y, p4.z, p4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w};
+        float ayv = 0.f, yh = 0.f, xf = 0.f;
+        if constexpr (RP) {
+            if (b != cached_b) {                          // warp-uniform: intrinsics change once per image
+                float fx, fy;
+                load_K(a, b, fx, fy, cxv, cyv);
+                fxe = fx + eps_r; fye = fy + eps_r;       // depth_loss.h:299-300
+                rfx = __frcp_rn(fxe); rfy = __frcp_rn(fye);
+                mk_ok = markstein_safe(fxe) && markstein_safe(fye);
+                cached_b = b;
+            }
+            ayv = (float)y - cyv;
+            yh = ayv * rfy;                               // d pY / d p, tolerance path
+            xf = (float)x;
+        }
+        float lp[4] = {0.f, 0.f, 0.f, 0.f}, lg[4] = {0.f, 0.f, 0.f, 0.f};
+        if constexpr (SI) {
+#pragma unroll
+            for (int k = 0; k < 4; k += 2) {
+                const float2 a2 = log_exact2(make_float2(clamp_nan(p[k], eps_s, 1000.0f), clamp_nan(p[k + 1], eps_s, 1000.0f)));
+                const float2 b2 = log_exact2(make_float2(clamp_nan(g[k], eps_s, 1000.0f), clamp_nan(g[k + 1], eps_s, 1000.0f)));
+                lp[k] = a2.x; lp[k + 1] = a2.y; lg[k] = b2.x; lg[k + 1] = b2.y;
+            }
+        }
+        float out[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float gsum = 0.f;
+            if constexpr (SI) {
+                const bool m = HAS_MASK ? um[k] : (g[k] > eps_s);
+                if (m && in_range_pos(p[k], eps_s, 1000.0f)) gsum = fmaf(c1, lp[k] - lg[k], c2) * rcp_approx(p[k]);
+            }
+            if constexpr (RP) {
+                const bool m = HAS_MASK ? um[k] : (g[k] > eps_r);
+                if (m) {
+                    const float ax = (xf + (float)k) - cxv;            // (float)(x+k) is exact; depth_loss.h:299
+                    float pX, gX, pY, gY;
+                    if (mk_ok) {
+                        pX = div_by_const(__fmul_rn(ax, p[k]), fxe, rfx);
+                        gX = div_by_const(__fmul_rn(ax, g[k]), fxe, rfx);
+                        pY = div_by_const(__fmul_rn(ayv, p[k]), fye, rfy);
+                        gY = div_by_const(__fmul_rn(ayv, g[k]), fye, rfy);
+                    } else {
+                        pX = __fdiv_rn(__fmul_rn(ax, p[k]), fxe);
+                        gX = __fdiv_rn(__fmul_rn(ax, g[k]), fxe);
+                        pY = __fdiv_rn(__fmul_rn(ayv, p[k]), fye);
+                        gY = __fdiv_rn(__fmul_rn(ayv, g[k]), fye);
+                    }
+                    const float dX = pX - gX, dY = pY - gY, dZ = p[k] - g[k];
+                    const float ss = fmaf(dZ, dZ, fmaf(dY, dY, dX * dX)) + eps_r;   // :313-315
+                    const float re = rsqrt_approx(ss);
+                    acc[BF_RP_E] = fmaf(ss, re, acc[BF_RP_E]);
+                    gsum = fmaf(fmaf(dX, ax * rfx, fmaf(dY, yh, dZ)) * re, rpn, gsum);
+                }
+            }
+            out[k] = gsum;
+        }
+        if (a.grad) *reinterpret_cast<float4*>(a.grad + off) = make_float4(out[0], out[1], out[2], out[3]);
+    }
+    if (publish_partials(a, acc, blockIdx.x, s_f, &s_last)) {
         finalize_results(a, s_d);
         if (tid == 0 && a.metrics) write_metric_results(a.stats, a.metrics, *a.results);
     }

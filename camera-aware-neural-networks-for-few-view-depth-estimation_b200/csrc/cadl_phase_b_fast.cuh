@@ -197,21 +197,21 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
                 const int c4 = pass * 32 + lane;
                 if (c4 < FRW / 4) {
                     const int gx = x0 - HALO + 4 * c4;
-                    float4 pv, gv;
+                    float* dp = sm.sp + rr * FRW + 4 * c4;
+                    float* dg = sm.sg + rr * FRW + 4 * c4;
                     if (gx >= 0 && gx + 3 < W) {
-                        pv = __ldg(reinterpret_cast<const float4*>(predb + rowo + gx));
-                        gv = __ldg(reinterpret_cast<const float4*>(gtb + rowo + gx));
+                        cp_async16(dp, predb + rowo + gx);
+                        cp_async16(dg, gtb + rowo + gx);
                     } else {   // whole float4 outside (W % 4 == 0): replicate the border pixel
                         const int cx = gx < 0 ? 0 : W - 1;
                         const float ps = __ldg(predb + rowo + cx), gs = __ldg(gtb + rowo + cx);
-                        pv = make_float4(ps, ps, ps, ps);
-                        gv = make_float4(gs, gs, gs, gs);
+                        *reinterpret_cast<float4*>(dp) = make_float4(ps, ps, ps, ps);
+                        *reinterpret_cast<float4*>(dg) = make_float4(gs, gs, gs, gs);
                     }
-                    *reinterpret_cast<float4*>(sm.sp + rr * FRW + 4 * c4) = pv;
-                    *reinterpret_cast<float4*>(sm.sg + rr * FRW + 4 * c4) = gv;
                 }
             }
         }
+        cp_async_wait_all();
         __syncthreads();
 
         // ---------------- P2: avg-pool pyramid in the reference's summation order, pooled logs ----------------
@@ -299,7 +299,8 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
         // ---- row state ----
         float pc[5], Ic[3][5];              // current row: own 4 + right neighbour
         float pn[5], In[3][5];              // next row (index 4 filled by finish_row once the loads have landed)
-        float hn_p = 0.f, hn_I[3] = {0.f, 0.f, 0.f};   // last lane's halo pixel of the next row
+        float hn_p = 0.f, hn_I[3] = {0.f, 0.f, 0.f};   // end lanes' halo pixel of the next row
+        float hc_p = 0.f, hc_I[3] = {0.f, 0.f, 0.f};   // ... of the current row
         float lpc[4] = {0.f, 0.f, 0.f, 0.f}, lgc[4] = {0.f, 0.f, 0.f, 0.f};   // logs of the current row
         float sy_up[4] = {0.f, 0.f, 0.f, 0.f}, ty_up[4] = {0.f, 0.f, 0.f, 0.f};
 
@@ -321,10 +322,16 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
                     if (in_img && lane_in) v = ldg_stream(reinterpret_cast<const float4*>(rgbb + c * plane + ro + gx0));
                     I[c][0] = v.x; I[c][1] = v.y; I[c][2] = v.z; I[c][3] = v.w;
                 }
-                if (lane == 31) {   // the right neighbour of the last lane lives in the next tile (or is replicated)
+                // the two lanes at the warp's ends also fetch the pixel beyond their end: lane 31 its right
+                // neighbour, lane 0 its left neighbour (same registers, different lanes)
+                if (lane == 31) {
                     hp = __ldg(predb + ro + gxr);
 #pragma unroll
                     for (int c = 0; c < 3; ++c) hI[c] = (in_img && right_in) ? __ldg(rgbb + c * plane + ro + gx0 + 4) : 0.f;
+                } else if (lane == 0 && gx0 >= 1) {
+                    hp = __ldg(predb + ro + gx0 - 1);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) hI[c] = in_img ? __ldg(rgbb + c * plane + ro + gx0 - 1) : 0.f;
                 }
             }
         };
@@ -387,6 +394,9 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
             }
         }
         finish_row(pn, In, hn_p, hn_I);
+        hc_p = hn_p;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) hc_I[c] = hn_I[c];
 #pragma unroll
         for (int k = 0; k < 5; ++k) pc[k] = pn[k];
 #pragma unroll
@@ -438,13 +448,9 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
                 float tl = __shfl_up_sync(0xffffffffu, tx[4], 1);
                 if (lane == 0) {
                     tl = 0.f;                                 // left neighbour lives in another tile: evaluate that edge here
-                    if (gx0 >= 1) {
-                        const int ro = gy * W;
-                        const float pl_ = __ldg(predb + ro + gx0 - 1);
-                        float s = 0.f;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) s += fabsf(Ic[c][0] - __ldg(rgbb + c * plane + ro + gx0 - 1));
-                        tl = ex2_approx(s * kExpScale) * sgn3(pc[0] - pl_);
+                    if (gx0 >= 1) {                           // (its pixel was fetched with the row: hc_p, hc_I)
+                        const float s = fabsf(Ic[0][0] - hc_I[0]) + fabsf(Ic[1][0] - hc_I[1]) + fabsf(Ic[2][0] - hc_I[2]);
+                        tl = ex2_approx(s * kExpScale) * sgn3(pc[0] - hc_p);
                     }
                 }
                 tx[0] = tl;
@@ -523,6 +529,9 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
 
             // roll the row state
             finish_row(pn, In, hn_p, hn_I);
+            hc_p = hn_p;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) hc_I[c] = hn_I[c];
 #pragma unroll
             for (int k = 0; k < 4; ++k) { sy_up[k] = sy_dn[k]; ty_up[k] = ty_dn[k]; lpc[k] = lpn[k]; lgc[k] = lgn[k]; }
 #pragma unroll

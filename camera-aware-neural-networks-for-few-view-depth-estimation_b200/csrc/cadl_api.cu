@@ -145,9 +145,19 @@ cudaError_t launch_fast(const PhaseBArgs& a, cudaStream_t st) {
 }
 
 template <int F>
-cudaError_t launch_point_fast(const PhaseBArgs& a, cudaStream_t st) {
-    if (a.mask) phase_b_point_fast_kernel<F, true><<<a.b_rows, kThreadsB, 0, st>>>(a);
-    else phase_b_point_fast_kernel<F, false><<<a.b_rows, kThreadsB, 0, st>>>(a);
+cudaError_t launch_point_fast(PhaseBArgs& a, cudaStream_t st) {
+    // (blocks per image, B) with ~8 CTAs per SM in total; a_rows = grid size (partial rows, ticket)
+    // whole rows per warp, as even as possible: rows_per_warp = round(H*B / (8 warps * ~8 CTAs * 148 SMs))
+    const int wpb = kThreadsB / 32;
+    int rpw = (int)(((long long)a.H * a.B + (148LL * 8 * wpb) / 2) / (148LL * 8 * wpb));
+    if (rpw < 1) rpw = 1;
+    int bpi = (a.H + wpb * rpw - 1) / (wpb * rpw);
+    while (bpi > 1 && bpi * a.B > kPointBlocks) --bpi;
+    if (bpi < 1) bpi = 1;
+    dim3 grid(bpi, a.B);
+    a.b_rows = bpi * a.B;
+    if (a.mask) phase_b_point_fast_kernel<F, true><<<grid, kThreadsB, 0, st>>>(a);
+    else phase_b_point_fast_kernel<F, false><<<grid, kThreadsB, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -194,23 +194,28 @@ __global__ void __launch_bounds__(kThreadsA, 4) phase_a_kernel(const PhaseAArgs 
         const float4* p4 = reinterpret_cast<const float4*>(a.pred + base);
         const float4* g4 = reinterpret_cast<const float4*>(a.gt + base);
         const uchar4* m4 = reinterpret_cast<const uchar4*>(a.mask ? a.mask + base : nullptr);
-        for (int i = v0 + tid; i < v1; i += 2 * kThreadsA) {
-            const int j = i + kThreadsA;
-            const bool hj = j < v1;
-            float4 p0 = make_float4(0, 0, 0, 0), p1 = p0, g0 = p0, g1 = p0;
-            uchar4 u0 = make_uchar4(1, 1, 1, 1), u1 = u0;
-            if (NEED_P) { p0 = __ldg(p4 + i); if (hj) p1 = __ldg(p4 + j); }
-            if (NEED_G) { g0 = __ldg(g4 + i); if (hj) g1 = __ldg(g4 + j); }
-            if (has_mask) { u0 = __ldg(m4 + i); if (hj) u1 = __ldg(m4 + j); }
-            {
-                const float pp[4] = {p0.x, p0.y, p0.z, p0.w}, gg[4] = {g0.x, g0.y, g0.z, g0.w};
-                const bool mm[4] = {u0.x != 0, u0.y != 0, u0.z != 0, u0.w != 0};
-                phase_a_quad<F, HAS_MASK>(pp, gg, mm, a, Lmin, Lmax, A, s_to);
+        // UNR independent 128-bit loads per tensor in flight per thread (light variants need more to cover DRAM latency)
+        constexpr int UNR = (F & (FA_EV | FA_TR)) ? 2 : 4;
+        for (int i = v0 + tid; i < v1; i += UNR * kThreadsA) {
+            float4 pv[UNR], gv[UNR];
+            uchar4 uv[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int j = i + u * kThreadsA;
+                pv[u] = make_float4(0, 0, 0, 0); gv[u] = pv[u]; uv[u] = make_uchar4(1, 1, 1, 1);
+                if (j < v1) {
+                    if (NEED_P) pv[u] = __ldg(p4 + j);
+                    if (NEED_G) gv[u] = __ldg(g4 + j);
+                    if (has_mask) uv[u] = __ldg(m4 + j);
+                }
             }
-            if (hj) {
-                const float pp[4] = {p1.x, p1.y, p1.z, p1.w}, gg[4] = {g1.x, g1.y, g1.z, g1.w};
-                const bool mm[4] = {u1.x != 0, u1.y != 0, u1.z != 0, u1.w != 0};
-                phase_a_quad<F, HAS_MASK>(pp, gg, mm, a, Lmin, Lmax, A, s_to);
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                if (i + u * kThreadsA < v1) {
+                    const float pp[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w}, gg[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+                    const bool mm[4] = {uv[u].x != 0, uv[u].y != 0, uv[u].z != 0, uv[u].w != 0};
+                    phase_a_quad<F, HAS_MASK>(pp, gg, mm, a, Lmin, Lmax, A, s_to);
+                }
             }
         }
     } else {
@@ -265,7 +270,7 @@ __global__ void __launch_bounds__(kThreadsA, 4) phase_a_kernel(const PhaseAArgs 
         if (lane == 0) s_iw[warp][q] = v;
     }
     const int blk = b * a.blocks_per_img + k;
-    if (tid < AF_COUNT) {
+    if ((F & ~FA_RP) && tid < AF_COUNT) {
         double acc = 0.0;
 #pragma unroll
         for (int w = 0; w < kThreadsA / 32; ++w) acc += (double)s_f[w][tid];
@@ -295,6 +300,9 @@ __global__ void __launch_bounds__(kThreadsA, 4) phase_a_kernel(const PhaseAArgs 
     const volatile double* part = a.a_part;
     for (int q = 0; q < AF_COUNT; ++q) {
         if (q == AF_PSUM) continue;
+        if (!(F & FA_SI) && (q == AF_SI_S || q == AF_SI_Q)) continue;
+        if (!(F & FA_EV) && q >= AF_EV_ABSREL && q <= AF_EV_SUMG) continue;
+        if (!(F & FA_TR) && q >= AF_TR_ABSREL && q <= AF_TR_LOGSQ) continue;
         double acc = 0.0;
         for (int i = tid; i < nblk; i += kThreadsA) acc += part[(size_t)i * AF_COUNT + q];
         double r = block_sum_double(acc, s_d);
@@ -321,6 +329,7 @@ __global__ void __launch_bounds__(kThreadsA, 4) phase_a_kernel(const PhaseAArgs 
         }
     }
     // per-image sum(pred): the blocks of image b are contiguous rows
+    if constexpr (F & FA_PSUM)
     for (int img = warp; img < a.B; img += kThreadsA / 32) {
         double acc = 0.0;
         for (int i = lane; i < a.blocks_per_img; i += 32)

@@ -577,16 +577,25 @@ __global__ void __launch_bounds__(kThreadsB) phase_b_point_fast_kernel(const Pha
 #pragma unroll
     for (int q = 0; q < BF_COUNT; ++q) acc[q] = 0.f;
 
+    // grid = (blocks per image, B): per-image constants once per CTA; a warp walks whole rows of its image
     const int H = a.H, W = a.W;
+    const int b = blockIdx.y;
     const int segs = (W + 127) >> 7;
-    const int items = a.B * H * segs;                    // < 2^31 (host-checked)
-    const int wstride = gridDim.x * (kThreadsB / 32);
-    int cached_b = -1;
     float fxe = 1.f, fye = 1.f, rfx = 1.f, rfy = 1.f, cxv = 0.f, cyv = 0.f;
     bool mk_ok = true;
-    for (int it = blockIdx.x * (kThreadsB / 32) + warp; it < items; it += wstride) {
-        const int row = it / segs, seg = it - row * segs;
-        const int b = row / H, y = row - b * H;
+    if constexpr (RP) {
+        float fx, fy;
+        load_K(a, b, fx, fy, cxv, cyv);
+        fxe = fx + eps_r; fye = fy + eps_r;               // depth_loss.h:299-300
+        rfx = __frcp_rn(fxe); rfy = __frcp_rn(fye);
+        mk_ok = markstein_safe(fxe) && markstein_safe(fye);
+    }
+    const int wstride = gridDim.x * (kThreadsB / 32);
+    for (int y = blockIdx.x * (kThreadsB / 32) + warp; y < H; y += wstride) {
+      const int row = b * H + y;
+      const float ayv = RP ? (float)y - cyv : 0.f;
+      const float yh = ayv * rfy;                         // d pY / d p, tolerance path
+      for (int seg = 0; seg < segs; ++seg) {
         const int x = (seg << 7) + 4 * lane;
         if (x >= W) continue;
         const int off = row * W + x;
@@ -598,20 +607,7 @@ __global__ void __launch_bounds__(kThreadsB) phase_b_point_fast_kernel(const Pha
             um[0] = u.x != 0; um[1] = u.y != 0; um[2] = u.z != 0; um[3] = u.w != 0;
         }
         const float p[4] = {p4.x, p4.y, p4.z, p4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w};
-        float ayv = 0.f, yh = 0.f, xf = 0.f;
-        if constexpr (RP) {
-            if (b != cached_b) {                          // warp-uniform: intrinsics change once per image
-                float fx, fy;
-                load_K(a, b, fx, fy, cxv, cyv);
-                fxe = fx + eps_r; fye = fy + eps_r;       // depth_loss.h:299-300
-                rfx = __frcp_rn(fxe); rfy = __frcp_rn(fye);
-                mk_ok = markstein_safe(fxe) && markstein_safe(fye);
-                cached_b = b;
-            }
-            ayv = (float)y - cyv;
-            yh = ayv * rfy;                               // d pY / d p, tolerance path
-            xf = (float)x;
-        }
+        const float xf = (float)x;
         float lp[4] = {0.f, 0.f, 0.f, 0.f}, lg[4] = {0.f, 0.f, 0.f, 0.f};
         if constexpr (SI) {
 #pragma unroll
@@ -655,8 +651,9 @@ __global__ void __launch_bounds__(kThreadsB) phase_b_point_fast_kernel(const Pha
             out[k] = gsum;
         }
         if (a.grad) *reinterpret_cast<float4*>(a.grad + off) = make_float4(out[0], out[1], out[2], out[3]);
+      }
     }
-    if (publish_partials(a, acc, blockIdx.x, s_f, &s_last)) {
+    if (publish_partials(a, acc, blockIdx.y * gridDim.x + blockIdx.x, s_f, &s_last)) {
         finalize_results(a, s_d);
         if (tid == 0 && a.metrics) write_metric_results(a.stats, a.metrics, *a.results);
     }

@@ -241,9 +241,10 @@ def metrics(pred, gt, mask=None, which: int = METRICS_EVAL | METRICS_TRAIN, min_
     return ws
 
 
-def force_generic(on: bool):
-    """Test hook: route phase B through the generic kernel even for aligned shapes."""
-    lib().cadl_debug_force_generic(1 if on else 0)
+def force_generic(on):
+    """Test hook (bit mask): 1 = route phase B through the generic kernel even for aligned shapes;
+    2 = keep the fast kernel but stage tiles with cp.async instead of TMA."""
+    lib().cadl_debug_force_generic(int(on))
 
 
 def selftest(which: int, lo_bits: int, hi_bits: int, param: float = 0.0, device="cuda:0") -> int:

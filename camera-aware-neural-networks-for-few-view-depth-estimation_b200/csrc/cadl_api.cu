@@ -69,7 +69,8 @@ struct Ws {
 };
 
 constexpr int kPointBlocks = 148 * 8;
-int g_force_generic = 0;   // cadl_debug_force_generic(): tests compare the two phase-B kernels
+int g_force_generic = 0;
+int g_force_no_tma = 0;     // bit 1 of cadl_debug_force_generic: keep the fast kernel but stage with cp.async   // cadl_debug_force_generic(): tests compare the two phase-B kernels
 
 WsLayout layout_for(int B, int H, int W) {
     WsLayout L = ws_layout(B, H, W);
@@ -127,8 +128,45 @@ cudaError_t launch_tile(const PhaseBArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// ---- TMA descriptors (cuTensorMapEncodeTiled through the runtime's driver entry point: no libcuda link) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)f;
+    }
+    return fn;
+}
+// (W, H, B) fp32 tensor, box = (FRW, FRH, 1), zero fill outside
+bool make_tile_map(CUtensorMap* m, const float* base, int B, int H, int W) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+    cuuint32_t box[3] = {(cuuint32_t)FRW, (cuuint32_t)FRH, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+struct TileMaps {
+    CUtensorMap pred, gt;
+    const float *pp = nullptr, *pg = nullptr;
+    int B = 0, H = 0, W = 0;
+    bool ok = false;
+};
+thread_local TileMaps g_maps;   // re-encoded only when a pointer or the shape changes
+
 template <int F, bool M>
-cudaError_t launch_fast_m(const PhaseBArgs& a, cudaStream_t st) {
+cudaError_t launch_fast_m(PhaseBArgs& a, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(phase_b_fast_kernel<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -136,11 +174,20 @@ cudaError_t launch_fast_m(const PhaseBArgs& a, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    phase_b_fast_kernel<F, M><<<a.b_rows, kThreadsB, kFastSmemBytes, st>>>(a);
+    a.use_tma = 0;
+    if ((F & FB_GRAD) && !g_force_no_tma) {
+        TileMaps& tm = g_maps;
+        if (!(tm.ok && tm.pp == a.pred && tm.pg == a.gt && tm.B == a.B && tm.H == a.H && tm.W == a.W)) {
+            tm.ok = make_tile_map(&tm.pred, a.pred, a.B, a.H, a.W) && make_tile_map(&tm.gt, a.gt, a.B, a.H, a.W);
+            tm.pp = a.pred; tm.pg = a.gt; tm.B = a.B; tm.H = a.H; tm.W = a.W;
+        }
+        a.use_tma = tm.ok ? 1 : 0;
+    }
+    phase_b_fast_kernel<F, M><<<a.b_rows, kThreadsB, kFastSmemBytes, st>>>(a, g_maps.pred, g_maps.gt);
     return cudaGetLastError();
 }
 template <int F>
-cudaError_t launch_fast(const PhaseBArgs& a, cudaStream_t st) {
+cudaError_t launch_fast(PhaseBArgs& a, cudaStream_t st) {
     return a.mask ? launch_fast_m<F, true>(a, st) : launch_fast_m<F, false>(a, st);
 }
 
@@ -313,7 +360,7 @@ void cadl_default_params(cadl_params* p) {
 }
 
 int cadl_version(void) { return CADL_VERSION; }
-void cadl_debug_force_generic(int on) { g_force_generic = on; }
+void cadl_debug_force_generic(int on) { g_force_generic = on & 1; g_force_no_tma = (on >> 1) & 1; }
 size_t cadl_sizeof_params(void) { return sizeof(cadl_params); }
 size_t cadl_sizeof_results(void) { return sizeof(cadl_results); }
 

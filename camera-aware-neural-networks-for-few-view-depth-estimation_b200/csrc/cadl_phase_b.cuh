@@ -41,6 +41,7 @@ struct PhaseBArgs {
     cadl_results* results;
     // host-computed 1/N of the means (depth_loss.h:162-163, :230-231); 0 where a mean has no element
     float inv_nx[4], inv_ny[4], sm_nx, sm_ny;
+    int use_tma;   // fast kernel: stage pred/gt with TMA box loads (tensor maps passed next to this struct)
 };
 
 // ---- shared-memory geometry of the tile kernel -------------------------------------------------
@@ -411,7 +412,7 @@ __global__ void __launch_bounds__(kThreadsB) phase_b_point_kernel(const PhaseBAr
 // ================================================================================================
 template <int F>
 __global__ void __launch_bounds__(kThreadsB, 2) phase_b_tile_kernel(const PhaseBArgs a) {
-    extern __shared__ __align__(16) float smem_raw[];
+    extern __shared__ __align__(128) float smem_raw[];
     __shared__ float s_f[kThreadsB / 32][BF_COUNT];
     __shared__ double s_d[8];
     __shared__ int s_last;

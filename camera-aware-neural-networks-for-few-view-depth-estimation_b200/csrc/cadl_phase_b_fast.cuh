@@ -18,6 +18,7 @@
 // CTA = 256 threads, tile 48 x 128; shared memory ~101 KB so two CTAs share an SM and one CTA's staging
 // overlaps the other's arithmetic.
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include "cadl_common.cuh"
 #include "cadl_math.cuh"
 #include "cadl_phase_a.cuh"
@@ -144,8 +145,11 @@ __device__ __forceinline__ void coef_pass(const PhaseBArgs& a, const FastSmem& s
 }
 
 template <int F, bool HAS_MASK>
-__global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseBArgs a) {
-    extern __shared__ __align__(16) float smem_raw[];
+__global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseBArgs a,
+                                                                    const __grid_constant__ CUtensorMap tm_pred,
+                                                                    const __grid_constant__ CUtensorMap tm_gt) {
+    extern __shared__ __align__(128) float smem_raw[];
+    __shared__ __align__(8) unsigned long long s_bar;
     __shared__ float s_f[kThreadsB / 32][BF_COUNT];
     __shared__ double s_d[8];
     __shared__ float s_c[8];
@@ -189,29 +193,55 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
     for (int q = 0; q < BF_COUNT; ++q) acc[q] = 0.f;
 
     if constexpr (GRAD) {
-        // ---------------- P1: stage raw pred / gt with an 8-pixel halo, edge pixels replicated ----------------
-        for (int rr = warp; rr < FRH; rr += kThreadsB / 32) {
-            const int rowo = clampi(y0 - HALO + rr, 0, H - 1) * W;
+        // ---------------- P1: stage raw pred / gt with an 8-pixel halo ----------------
+        if (a.use_tma) {
+            // TMA: one thread issues two 3-D box loads (144 x 64 x 1 floats each); pixels outside the image
+            // arrive as zeros.  Only the 1-pixel ring around the image needs the replicated border value
+            // (pooled cells outside the image are invalid anyway), so border tiles patch one row / column.
+            if (tid == 0) mbar_init(&s_bar, 1);
+            __syncthreads();
+            if (tid == 0) {
+                mbar_expect_tx(&s_bar, 2u * FRH * FRW * sizeof(float));
+                tma_load_3d(sm.sp, &tm_pred, x0 - HALO, y0 - HALO, b, &s_bar);
+                tma_load_3d(sm.sg, &tm_gt, x0 - HALO, y0 - HALO, b, &s_bar);
+            }
+            mbar_wait(&s_bar, 0);
+            const int r_top = (y0 == 0) ? HALO - 1 : -1;                       // staged row of image row -1
+            const int r_bot = (H - y0 + HALO < FRH) ? H - y0 + HALO : -1;      // staged row of image row H
+            const int c_lft = (x0 == 0) ? HALO - 1 : -1;
+            const int c_rgt = (W - x0 + HALO < FRW) ? W - x0 + HALO : -1;
+            if (r_top >= 0 || r_bot >= 0 || c_lft >= 0 || c_rgt >= 0) {       // block-uniform: the tile touches the border
+                if (r_top >= 0 && tid < FRW) { sm.sp[r_top * FRW + tid] = sm.sp[(r_top + 1) * FRW + tid]; sm.sg[r_top * FRW + tid] = sm.sg[(r_top + 1) * FRW + tid]; }
+                if (r_bot >= 0 && tid < FRW) { sm.sp[r_bot * FRW + tid] = sm.sp[(r_bot - 1) * FRW + tid]; sm.sg[r_bot * FRW + tid] = sm.sg[(r_bot - 1) * FRW + tid]; }
+                __syncthreads();                                               // rows first, then columns (corners follow)
+                if (c_lft >= 0 && tid < FRH) { sm.sp[tid * FRW + c_lft] = sm.sp[tid * FRW + c_lft + 1]; sm.sg[tid * FRW + c_lft] = sm.sg[tid * FRW + c_lft + 1]; }
+                if (c_rgt >= 0 && tid < FRH) { sm.sp[tid * FRW + c_rgt] = sm.sp[tid * FRW + c_rgt - 1]; sm.sg[tid * FRW + c_rgt] = sm.sg[tid * FRW + c_rgt - 1]; }
+            }
+        } else {
+            // cp.async fallback (no tensor maps): 16-byte copies, border pixels replicated
+            for (int rr = warp; rr < FRH; rr += kThreadsB / 32) {
+                const int rowo = clampi(y0 - HALO + rr, 0, H - 1) * W;
 #pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                const int c4 = pass * 32 + lane;
-                if (c4 < FRW / 4) {
-                    const int gx = x0 - HALO + 4 * c4;
-                    float* dp = sm.sp + rr * FRW + 4 * c4;
-                    float* dg = sm.sg + rr * FRW + 4 * c4;
-                    if (gx >= 0 && gx + 3 < W) {
-                        cp_async16(dp, predb + rowo + gx);
-                        cp_async16(dg, gtb + rowo + gx);
-                    } else {   // whole float4 outside (W % 4 == 0): replicate the border pixel
-                        const int cx = gx < 0 ? 0 : W - 1;
-                        const float ps = __ldg(predb + rowo + cx), gs = __ldg(gtb + rowo + cx);
-                        *reinterpret_cast<float4*>(dp) = make_float4(ps, ps, ps, ps);
-                        *reinterpret_cast<float4*>(dg) = make_float4(gs, gs, gs, gs);
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int c4 = pass * 32 + lane;
+                    if (c4 < FRW / 4) {
+                        const int gx = x0 - HALO + 4 * c4;
+                        float* dp = sm.sp + rr * FRW + 4 * c4;
+                        float* dg = sm.sg + rr * FRW + 4 * c4;
+                        if (gx >= 0 && gx + 3 < W) {
+                            cp_async16(dp, predb + rowo + gx);
+                            cp_async16(dg, gtb + rowo + gx);
+                        } else {   // whole float4 outside (W % 4 == 0): replicate the border pixel
+                            const int cx = gx < 0 ? 0 : W - 1;
+                            const float ps = __ldg(predb + rowo + cx), gs = __ldg(gtb + rowo + cx);
+                            *reinterpret_cast<float4*>(dp) = make_float4(ps, ps, ps, ps);
+                            *reinterpret_cast<float4*>(dg) = make_float4(gs, gs, gs, gs);
+                        }
                     }
                 }
             }
+            cp_async_wait_all();
         }
-        cp_async_wait_all();
         __syncthreads();
 
         // ---------------- P2: avg-pool pyramid in the reference's summation order, pooled logs ----------------
@@ -284,7 +314,7 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 axk[k] = (float)(gx0 + k) - cxv;
-                xhk[k] = __fdiv_rn(axk[k], fxe);
+                xhk[k] = axk[k] * rfx;                       // d pX / d p: tolerance path
             }
         }
         const float inx0 = a.inv_nx[0] * 0.25f * a.w_grad * up, iny0 = a.inv_ny[0] * 0.25f * a.w_grad * up;
@@ -295,6 +325,9 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
         constexpr float kExpScale = -1.4426950408889634f / 3.0f;    // exp(-mean_c|dI|) = 2^(kExpScale * sum_c|dI|)
         const int gxr = clampi(gx0 + 4, 0, W - 1);                  // right neighbour column of the last lane
         const bool right_in = gx0 + 4 < W;
+        const bool endlane = (lane == 31) || (lane == 0 && gx0 >= 1);
+        const int hx = (lane == 31) ? gxr : (gx0 >= 1 ? gx0 - 1 : 0);     // column of the end lanes' halo pixel
+        const bool h_rgb_ok = (lane == 31) ? right_in : true;
 
         // ---- row state ----
         float pc[5], Ic[3][5];              // current row: own 4 + right neighbour
@@ -323,15 +356,12 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
                     I[c][0] = v.x; I[c][1] = v.y; I[c][2] = v.z; I[c][3] = v.w;
                 }
                 // the two lanes at the warp's ends also fetch the pixel beyond their end: lane 31 its right
-                // neighbour, lane 0 its left neighbour (same registers, different lanes)
-                if (lane == 31) {
-                    hp = __ldg(predb + ro + gxr);
+                // neighbour, lane 0 its left neighbour (same registers, same instructions, different lanes)
+                if (endlane) {
+                    hp = __ldg(predb + ro + hx);
+                    const bool ok = in_img && h_rgb_ok;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) hI[c] = (in_img && right_in) ? __ldg(rgbb + c * plane + ro + gx0 + 4) : 0.f;
-                } else if (lane == 0 && gx0 >= 1) {
-                    hp = __ldg(predb + ro + gx0 - 1);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) hI[c] = in_img ? __ldg(rgbb + c * plane + ro + gx0 - 1) : 0.f;
+                    for (int c = 0; c < 3; ++c) hI[c] = ok ? __ldg(rgbb + c * plane + ro + hx) : 0.f;
                 }
             }
         };

@@ -59,12 +59,11 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 
 // Sums of one 8x8 block for scale S (cells of f x f, f = 2^S), row-major sequential inside each window --
 // the loop order of ATen's avg_pool2d on CPU and CUDA -- then log(clamp(.)) on the packed pipes.
-template <int S>
-__device__ __forceinline__ void pool_scale(const float (&v)[8][8], const PhaseBArgs& a, float* cc, float* dst, int t,
-                                           int by, int bx, int y0, int x0, int H, int W) {
+// INTERIOR blocks store all their cells unconditionally; halo blocks only the cells next to the tile.
+template <int S, bool INTERIOR>
+__device__ __forceinline__ void pool_scale(const float (&v)[8][8], float eps, float* cc, float* dst, int t, int by, int bx) {
     constexpr int f = 1 << S, nc = 8 >> S;
     constexpr float inv_area = 1.0f / (float)(f * f);
-    const int Hs = H >> S, Ws = W >> S;
     float q[nc][nc];
 #pragma unroll
     for (int ci = 0; ci < nc; ++ci)
@@ -77,67 +76,94 @@ __device__ __forceinline__ void pool_scale(const float (&v)[8][8], const PhaseBA
                 for (int c = 0; c < f; ++c) sum += v[ci * f + r][cj * f + c];
             q[ci][cj] = sum * inv_area;      // sum / (f*f): exact power-of-two scaling
         }
-    float ql[nc][nc];
-    if constexpr (nc == 1) {
-        ql[0][0] = log_exact(clamp_nan(q[0][0], a.eps_grad, 1000.0f));
+    // local cell coordinates of this block's first cell (the staged region starts one coarsest cell before the tile)
+    const int cy0 = by * nc - nc, cx0 = bx * nc - nc;
+    if constexpr (INTERIOR) {
+        float* drow = dst + fpool_off(S) + (cy0 + 1) * fpool_w(S) + (cx0 + 1);
+        float* crow = cc + fcc_off(S) + cy0 * fcc_w(S) + cx0;
+#pragma unroll
+        for (int ci = 0; ci < nc; ++ci) {
+            if constexpr (nc == 1) {
+                drow[0] = log_exact(clamp_nan(q[0][0], eps, 1000.0f));
+            } else {
+#pragma unroll
+                for (int cj = 0; cj < nc; cj += 2) {
+                    const float2 l2 = log_exact2(make_float2(clamp_nan(q[ci][cj], eps, 1000.0f), clamp_nan(q[ci][cj + 1], eps, 1000.0f)));
+                    drow[ci * fpool_w(S) + cj] = l2.x;       // (odd float index: the array has a 1-cell halo)
+                    drow[ci * fpool_w(S) + cj + 1] = l2.y;
+                }
+            }
+            if (t == 0) {
+#pragma unroll
+                for (int cj = 0; cj < nc; ++cj)
+                    crow[ci * fcc_w(S) + cj] = in_range_pos(q[ci][cj], eps, 1000.0f) ? rcp_approx(q[ci][cj]) : 0.f;
+            }
+        }
     } else {
 #pragma unroll
         for (int ci = 0; ci < nc; ++ci)
 #pragma unroll
-            for (int cj = 0; cj < nc; cj += 2) {
-                const float2 l2 = log_exact2(make_float2(clamp_nan(q[ci][cj], a.eps_grad, 1000.0f),
-                                                         clamp_nan(q[ci][cj + 1], a.eps_grad, 1000.0f)));
-                ql[ci][cj] = l2.x;
-                ql[ci][cj + 1] = l2.y;
+            for (int cj = 0; cj < nc; ++cj) {
+                const int cy = cy0 + ci, cx = cx0 + cj;
+                if (cy < -1 || cy > (FTH >> S) || cx < -1 || cx > (FTW >> S)) continue;
+                dst[fpool_off(S) + (cy + 1) * fpool_w(S) + (cx + 1)] = log_exact(clamp_nan(q[ci][cj], eps, 1000.0f));
             }
     }
-#pragma unroll
-    for (int ci = 0; ci < nc; ++ci)
-#pragma unroll
-        for (int cj = 0; cj < nc; ++cj) {
-            const int cy = by * nc + ci - (HALO >> S);
-            const int cx = bx * nc + cj - (HALO >> S);
-            if (cy < -1 || cy > (FTH >> S) || cx < -1 || cx > (FTW >> S)) continue;
-            const int gyc = (y0 >> S) + cy, gxc = (x0 >> S) + cx;
-            const bool valid = gyc >= 0 && gyc < Hs && gxc >= 0 && gxc < Ws;
-            dst[fpool_off(S) + (cy + 1) * fpool_w(S) + (cx + 1)] = valid ? ql[ci][cj] : 0.f;
-            if (t == 0 && cy >= 0 && cy < (FTH >> S) && cx >= 0 && cx < (FTW >> S)) {
-                const float qq = q[ci][cj];
-                const bool cm = (qq >= a.eps_grad) && (qq <= 1000.0f);
-                cc[fcc_off(S) + cy * fcc_w(S) + cx] = (valid && cm) ? rcp_approx(qq) : 0.f;
-            }
-        }
 }
 
-// One scale's per-cell coefficient pass: every cell evaluates its four edges (the two it owns also feed the
-// loss sum) and stores coefficient * (1/q) * spread [+ the two coarser scales when GATHER].
+// Border tiles: copy the pooled logs of the last valid row / column of cells into the first row / column
+// outside the image, so that an edge across the image border has residual exactly 0 (no per-edge predicates).
+template <int S>
+__device__ __forceinline__ void pooled_replicate(const PhaseBArgs& a, const FastSmem& sm, int tid, int y0, int x0, bool rows) {
+    constexpr int ch = FTH >> S, cw = FTW >> S, pw = cw + 2, ph = ch + 2;
+    const int Hs = a.H >> S, Ws = a.W >> S;
+    float* PL = sm.pl + fpool_off(S);
+    float* PG = sm.pg + fpool_off(S);
+    if (rows) {
+        const int top = (y0 == 0) ? 0 : -1;                                  // array row of cells at image row -1
+        const int bot = (Hs - (y0 >> S) <= ch) ? Hs - (y0 >> S) + 1 : -1;    // array row of cells at image row Hs
+        for (int i = tid; i < pw; i += kThreadsB) {
+            if (top >= 0) { PL[top * pw + i] = PL[(top + 1) * pw + i]; PG[top * pw + i] = PG[(top + 1) * pw + i]; }
+            if (bot >= 0) { PL[bot * pw + i] = PL[(bot - 1) * pw + i]; PG[bot * pw + i] = PG[(bot - 1) * pw + i]; }
+        }
+    } else {
+        const int lft = (x0 == 0) ? 0 : -1;
+        const int rgt = (Ws - (x0 >> S) <= cw) ? Ws - (x0 >> S) + 1 : -1;
+        for (int i = tid; i < ph; i += kThreadsB) {
+            if (lft >= 0) { PL[i * pw + lft] = PL[i * pw + lft + 1]; PG[i * pw + lft] = PG[i * pw + lft + 1]; }
+            if (rgt >= 0) { PL[i * pw + rgt] = PL[i * pw + rgt - 1]; PG[i * pw + rgt] = PG[i * pw + rgt - 1]; }
+        }
+    }
+}
+
+// One scale's per-cell coefficient pass (branch-free): every cell evaluates its four edges, the two it owns
+// also feed the loss sum; stores coefficient * (1/q) * spread [+ the two coarser scales when GATHER].
+// Cells outside the image hold 1/q = 0, and edges across the border vanish by replication (above).
 template <int S, bool GATHER>
 __device__ __forceinline__ void coef_pass(const PhaseBArgs& a, const FastSmem& sm, int tid, int y0, int x0, float spread,
                                           float& acc_x, float& acc_y) {
     constexpr int ch = FTH >> S, cw = FTW >> S, pw = (FTW >> S) + 2;
     const int Hs = a.H >> S, Ws = a.W >> S;
-    const float inv_nx = a.inv_nx[S], inv_ny = a.inv_ny[S];
+    const float inv_nx = a.inv_nx[S] * spread, inv_ny = a.inv_ny[S] * spread;
     const float* PL = sm.pl + fpool_off(S);
     const float* PG = sm.pg + fpool_off(S);
     float* CC = sm.cc + fcc_off(S);
     const float* C2 = sm.cc + fcc_off(2);
     const float* C3 = sm.cc + fcc_off(3);
     float ax = 0.f, ay = 0.f;
+#pragma unroll 2
     for (int i = tid; i < ch * cw; i += kThreadsB) {
-        const int cy = i / cw, cx = i - cy * cw;
-        const int gyc = (y0 >> S) + cy, gxc = (x0 >> S) + cx;
-        float coef = 0.f;
-        if (gyc < Hs && gxc < Ws) {
-            const int c = (cy + 1) * pw + (cx + 1);
-            const float lp = PL[c], lg = PG[c];
-            float sx_r = 0.f, sx_l = 0.f, sy_d = 0.f, sy_u = 0.f;
-            if (gxc + 1 < Ws) { const float e = (PL[c + 1] - lp) - (PG[c + 1] - lg); ax += fabsf(e); sx_r = sgn3(e); }   // :140-148,162
-            if (gxc >= 1) sx_l = sgn3((lp - PL[c - 1]) - (lg - PG[c - 1]));
-            if (gyc + 1 < Hs) { const float e = (PL[c + pw] - lp) - (PG[c + pw] - lg); ay += fabsf(e); sy_d = sgn3(e); } // :151-159,163
-            if (gyc >= 1) sy_u = sgn3((lp - PL[c - pw]) - (lg - PG[c - pw]));
-            coef = ((sx_l - sx_r) * inv_nx + (sy_u - sy_d) * inv_ny) * CC[i] * spread;
-            if constexpr (GATHER) coef += C2[(cy >> 1) * fcc_w(2) + (cx >> 1)] + C3[(cy >> 2) * fcc_w(3) + (cx >> 2)];
-        }
+        const int cy = i / cw, cx = i - cy * cw;                  // cw is a power of two
+        const bool cv = ((y0 >> S) + cy < Hs) && ((x0 >> S) + cx < Ws);
+        const int c = (cy + 1) * pw + (cx + 1);
+        const float lp = PL[c], lg = PG[c];
+        const float e_r = (PL[c + 1] - lp) - (PG[c + 1] - lg);    // depth_loss.h:140-148,162
+        const float e_l = (lp - PL[c - 1]) - (lg - PG[c - 1]);
+        const float e_d = (PL[c + pw] - lp) - (PG[c + pw] - lg);  // :151-159,163
+        const float e_u = (lp - PL[c - pw]) - (lg - PG[c - pw]);
+        if (cv) { ax += fabsf(e_r); ay += fabsf(e_d); }
+        float coef = ((sgn3(e_l) - sgn3(e_r)) * inv_nx + (sgn3(e_u) - sgn3(e_d)) * inv_ny) * CC[i];
+        if constexpr (GATHER) coef += C2[(cy >> 1) * fcc_w(2) + (cx >> 1)] + C3[(cy >> 2) * fcc_w(3) + (cx >> 2)];
         CC[i] = coef;
     }
     acc_x += ax;
@@ -247,12 +273,46 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
         // ---------------- P2: avg-pool pyramid in the reference's summation order, pooled logs ----------------
         {
             constexpr int BR = FRH / 8, BC = FRW / 8;   // 8 x 18 blocks of 8x8
+            // items 0..191: interior blocks (6 x 16 per tensor) -- six whole warps on the unconditional path;
+            // items 192..287: the ring of halo blocks (48 per tensor)
+            constexpr int NI = (BR - 2) * (BC - 2), NH = BR * BC - NI;
             for (int item = tid; item < 2 * BR * BC; item += kThreadsB) {
-                const int t = item >= BR * BC ? 1 : 0;
-                const int blk = item - t * (BR * BC);
-                const int by = blk / BC, bx = blk - by * BC;
-                const float* src = (t == 0 ? sm.sp : sm.sg) + (by * 8) * FRW + bx * 8;
+                int t, by, bx;
+                if (item < 2 * NI) {
+                    t = item >= NI ? 1 : 0;
+                    const int idx = item - t * NI;
+                    by = 1 + idx / (BC - 2);
+                    bx = 1 + idx - (by - 1) * (BC - 2);
+                } else {
+                    const int h = item - 2 * NI;
+                    t = h >= NH ? 1 : 0;
+                    const int idx = h - t * NH;
+                    if (idx < BC) { by = 0; bx = idx; }
+                    else if (idx < 2 * BC) { by = BR - 1; bx = idx - BC; }
+                    else if (idx < 2 * BC + (BR - 2)) { by = 1 + idx - 2 * BC; bx = 0; }
+                    else { by = 1 + idx - 2 * BC - (BR - 2); bx = BC - 1; }
+                }
                 float* dst = (t == 0 ? sm.pl : sm.pg);
+                // H, W and the block origin are multiples of 8: a block is entirely inside or outside the image
+                const int gby = y0 - HALO + 8 * by, gbx = x0 - HALO + 8 * bx;
+                const bool valid = gby >= 0 && gby < H && gbx >= 0 && gbx < W;
+                const bool interior = by >= 1 && by <= BR - 2 && bx >= 1 && bx <= BC - 2;
+                if (!valid) {   // cells outside the image: defined but inert (1/q = 0; logs patched by pooled_replicate)
+#pragma unroll
+                    for (int S = 1; S <= 3; ++S) {
+                        const int nc = 8 >> S, cy0 = by * nc - nc, cx0 = bx * nc - nc;
+                        for (int ci = 0; ci < nc; ++ci)
+                            for (int cj = 0; cj < nc; ++cj) {
+                                const int cy = cy0 + ci, cx = cx0 + cj;
+                                if (cy < -1 || cy > (FTH >> S) || cx < -1 || cx > (FTW >> S)) continue;
+                                dst[fpool_off(S) + (cy + 1) * fpool_w(S) + (cx + 1)] = 0.f;
+                                if (t == 0 && cy >= 0 && cy < (FTH >> S) && cx >= 0 && cx < (FTW >> S))
+                                    sm.cc[fcc_off(S) + cy * fcc_w(S) + cx] = 0.f;
+                            }
+                    }
+                    continue;
+                }
+                const float* src = (t == 0 ? sm.sp : sm.sg) + (by * 8) * FRW + bx * 8;
                 float v[8][8];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
@@ -261,12 +321,28 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
                     v[r][0] = lo.x; v[r][1] = lo.y; v[r][2] = lo.z; v[r][3] = lo.w;
                     v[r][4] = hi.x; v[r][5] = hi.y; v[r][6] = hi.z; v[r][7] = hi.w;
                 }
-                pool_scale<1>(v, a, sm.cc, dst, t, by, bx, y0, x0, H, W);
-                pool_scale<2>(v, a, sm.cc, dst, t, by, bx, y0, x0, H, W);
-                pool_scale<3>(v, a, sm.cc, dst, t, by, bx, y0, x0, H, W);
+                if (interior) {
+                    pool_scale<1, true>(v, a.eps_grad, sm.cc, dst, t, by, bx);
+                    pool_scale<2, true>(v, a.eps_grad, sm.cc, dst, t, by, bx);
+                    pool_scale<3, true>(v, a.eps_grad, sm.cc, dst, t, by, bx);
+                } else {
+                    pool_scale<1, false>(v, a.eps_grad, sm.cc, dst, t, by, bx);
+                    pool_scale<2, false>(v, a.eps_grad, sm.cc, dst, t, by, bx);
+                    pool_scale<3, false>(v, a.eps_grad, sm.cc, dst, t, by, bx);
+                }
             }
         }
         __syncthreads();
+        if (y0 == 0 || x0 == 0 || H - y0 <= FTH || W - x0 <= FTW) {   // block-uniform: the tile touches the image border
+            pooled_replicate<1>(a, sm, tid, y0, x0, true);
+            pooled_replicate<2>(a, sm, tid, y0, x0, true);
+            pooled_replicate<3>(a, sm, tid, y0, x0, true);
+            __syncthreads();
+            pooled_replicate<1>(a, sm, tid, y0, x0, false);
+            pooled_replicate<2>(a, sm, tid, y0, x0, false);
+            pooled_replicate<3>(a, sm, tid, y0, x0, false);
+            __syncthreads();
+        }
 
         // ---------------- P3a: coefficients of scales 3 and 2 ----------------
         const float wg = 0.25f * a.w_grad * up;              // 1/num_scales * weight * upstream

@@ -12,7 +12,7 @@ B=32 images of 480x640 per GPU (BASELINE config 3).  Prints ONE JSON line (rank 
   e2e       the same metric through the reference-facing C++ API (drop-in CombinedDepthLoss +
             DepthMetrics via host/libcadl_host.so) with pinned HOST buffers: H2D of pred/gt/rgb/K and the
             D2H of the loss scalar + metric blocks are inside the timed region
-  roofline  for the dominant kernel (phase_b_tile_kernel): algorithmic bytes (24 B/px: read pred, gt,
+  roofline  for the dominant kernel (phase_b_fast_kernel): algorithmic bytes (24 B/px: read pred, gt,
             3 x rgb, write grad) / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the unmodified reference headers on LibTorch CPU (oracle/_ref) timed on this box
 
@@ -242,7 +242,7 @@ def main():
 
     peak, peak_src = hbm_peak()
     achieved = ALGO_BYTES_PER_PX * P / (ms_b * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "phase_b_tile_kernel<15> (+ smooth_offset_kernel)",
+    roofline = {"bound": "hbm", "kernel": "phase_b_fast_kernel<15,false> (+ smooth_offset_kernel)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX * P,
@@ -315,7 +315,7 @@ def main():
                        "l2": "inputs+gradient 275 MB per step > 126 MB L2 (no flush needed)",
                        "seed": "1234 + rank"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": 3 * args.steps, "launches_per_step": ["phase_a_kernel<31>", "phase_b_tile_kernel<15>",
+            "gpu_launches": 3 * args.steps, "launches_per_step": ["phase_a_kernel<31,false>", "phase_b_fast_kernel<15,false>",
                                                                    "smooth_offset_kernel"],
             "clocks": clocks, "also": reproj,
         }

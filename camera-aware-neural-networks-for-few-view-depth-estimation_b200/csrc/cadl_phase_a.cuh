@@ -50,7 +50,7 @@ struct AccA {
     float c_absrel, c_sqrel, c_sq, c_logsq;          // eval == train
     unsigned c_n, c_c1, c_c2, c_c3;
     float e_abs, e_l10, e_sump, e_sumg;              // eval-only quantities
-    float t_logsq;                                   // train: sum (ld + first-order 1e-8 correction)^2
+    float t_logsq;                                   // train: correction of sum ld^2 for the +1e-8 inside the logs
 };
 constexpr int kToSlots = 8;   // train-only slow path: absrel, sqrel, sq, logsq, n, c1, c2, c3
 
@@ -61,12 +61,10 @@ __device__ __forceinline__ void phase_a_px(float p, float g, float lp, float lg,
     if constexpr (F & FA_SI) {
         // depth_loss.h:38-47
         const bool m = HAS_MASK ? um : (g > a.eps_si);
-        const float d = lp - lg;
-        if (m) {
-            A.si_n += 1u;
-            A.si_s += d;
-            A.si_q = fmaf(d, d, A.si_q);
-        }
+        const float d = m ? lp - lg : 0.f;
+        A.si_n += m ? 1u : 0u;
+        A.si_s += d;
+        A.si_q = fmaf(d, d, A.si_q);
     }
     if constexpr (F & FA_RP) {
         const bool m = HAS_MASK ? um : (g > a.eps_rp);      // depth_loss.h:318-320
@@ -99,12 +97,13 @@ __device__ __forceinline__ void phase_a_px(float p, float g, float lp, float lg,
                 A.e_sumg += g;
             }
             if constexpr (TR) {
-                if (pc == p) {
-                    // trainer :429: log(x + 1e-8).  (x + 1e-8f) - x is exact, so log(x + dx) = log x + dx/x to
-                    // well below one ulp; dx is 0 for x >= 0.25.
+                // trainer :429: log(x + 1e-8).  Only x < 0.25 changes under +1e-8f (half an ulp of 0.25 is 1.5e-8);
+                // there (x + 1e-8f) - x is exact and log(x + dx) = log x + dx/x to far below one ulp, so the train
+                // variant adds  (ld + c)^2 - ld^2 = c (2 ld + c)  to the common sum.  Rare branch.
+                if ((p < 0.25f || g < 0.25f) && pc == p) {
                     const float dp = (p + 1e-8f) - p, dg = (g + 1e-8f) - g;
-                    const float ldt = ld + fmaf(dp, rcp_approx(p), -dg * rg);
-                    A.t_logsq = fmaf(ldt, ldt, A.t_logsq);
+                    const float c = fmaf(dp, rcp_approx(p), -dg * rg);
+                    A.t_logsq = fmaf(c, fmaf(2.f, ld, c), A.t_logsq);
                 }
             }
         }
@@ -195,7 +194,7 @@ __global__ void __launch_bounds__(kThreadsA, 4) phase_a_kernel(const PhaseAArgs 
         const float4* g4 = reinterpret_cast<const float4*>(a.gt + base);
         const uchar4* m4 = reinterpret_cast<const uchar4*>(a.mask ? a.mask + base : nullptr);
         // UNR independent 128-bit loads per tensor in flight per thread (light variants need more to cover DRAM latency)
-        constexpr int UNR = (F & (FA_EV | FA_TR)) ? 2 : 4;
+        constexpr int UNR = (F & (FA_EV | FA_TR)) ? 2 : ((F == FA_RP) ? 8 : 4);
         for (int i = v0 + tid; i < v1; i += UNR * kThreadsA) {
             float4 pv[UNR], gv[UNR];
             uchar4 uv[UNR];
@@ -246,7 +245,7 @@ __global__ void __launch_bounds__(kThreadsA, 4) phase_a_kernel(const PhaseAArgs 
     af[AF_TR_ABSREL] = TRc ? A.c_absrel + s_to[0 * kThreadsA + tid] : 0.f;
     af[AF_TR_SQREL] = TRc ? A.c_sqrel + s_to[1 * kThreadsA + tid] : 0.f;
     af[AF_TR_SQ] = TRc ? A.c_sq + s_to[2 * kThreadsA + tid] : 0.f;
-    af[AF_TR_LOGSQ] = TRc ? A.t_logsq + s_to[3 * kThreadsA + tid] : 0.f;
+    af[AF_TR_LOGSQ] = TRc ? A.c_logsq + A.t_logsq + s_to[3 * kThreadsA + tid] : 0.f;
     ai[AI_SI_N] = A.si_n; ai[AI_RP_N] = A.rp_n;
     ai[AI_EV_N] = EVc ? A.c_n : 0u; ai[AI_EV_C1] = EVc ? A.c_c1 : 0u;
     ai[AI_EV_C2] = EVc ? A.c_c2 : 0u; ai[AI_EV_C3] = EVc ? A.c_c3 : 0u;

@@ -701,62 +701,73 @@ __global__ void __launch_bounds__(kThreadsB) phase_b_point_fast_kernel(const Pha
       const int row = b * H + y;
       const float ayv = RP ? (float)y - cyv : 0.f;
       const float yh = ayv * rfy;                         // d pY / d p, tolerance path
-      for (int seg = 0; seg < segs; ++seg) {
-        const int x = (seg << 7) + 4 * lane;
-        if (x >= W) continue;
-        const int off = row * W + x;
-        const float4 p4 = __ldg(reinterpret_cast<const float4*>(a.pred + off));
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.gt + off));
-        bool um[4] = {true, true, true, true};
-        if constexpr (HAS_MASK) {
-            const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(a.mask + off));
-            um[0] = u.x != 0; um[1] = u.y != 0; um[2] = u.z != 0; um[3] = u.w != 0;
+      // NB row segments (128 px each) per batch: all loads of a batch are issued before any arithmetic
+      constexpr int NB = 3;
+      for (int seg0 = 0; seg0 < segs; seg0 += NB) {
+        float4 p4[NB], g4[NB];
+        uchar4 u4[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const int x = ((seg0 + j) << 7) + 4 * lane;
+          p4[j] = make_float4(1.f, 1.f, 1.f, 1.f); g4[j] = make_float4(0.f, 0.f, 0.f, 0.f); u4[j] = make_uchar4(0, 0, 0, 0);
+          if (seg0 + j < segs && x < W) {
+            p4[j] = __ldg(reinterpret_cast<const float4*>(a.pred + row * W + x));
+            g4[j] = __ldg(reinterpret_cast<const float4*>(a.gt + row * W + x));
+            if constexpr (HAS_MASK) u4[j] = __ldg(reinterpret_cast<const uchar4*>(a.mask + row * W + x));
+          }
         }
-        const float p[4] = {p4.x, p4.y, p4.z, p4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w};
-        const float xf = (float)x;
-        float lp[4] = {0.f, 0.f, 0.f, 0.f}, lg[4] = {0.f, 0.f, 0.f, 0.f};
-        if constexpr (SI) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const int x = ((seg0 + j) << 7) + 4 * lane;
+          if (!(seg0 + j < segs && x < W)) continue;
+          const int off = row * W + x;
+          const bool um[4] = {u4[j].x != 0, u4[j].y != 0, u4[j].z != 0, u4[j].w != 0};
+          const float p[4] = {p4[j].x, p4[j].y, p4[j].z, p4[j].w}, g[4] = {g4[j].x, g4[j].y, g4[j].z, g4[j].w};
+          const float xf = (float)x;
+          float lp[4] = {0.f, 0.f, 0.f, 0.f}, lg[4] = {0.f, 0.f, 0.f, 0.f};
+          if constexpr (SI) {
 #pragma unroll
             for (int k = 0; k < 4; k += 2) {
-                const float2 a2 = log_exact2(make_float2(clamp_nan(p[k], eps_s, 1000.0f), clamp_nan(p[k + 1], eps_s, 1000.0f)));
-                const float2 b2 = log_exact2(make_float2(clamp_nan(g[k], eps_s, 1000.0f), clamp_nan(g[k + 1], eps_s, 1000.0f)));
-                lp[k] = a2.x; lp[k + 1] = a2.y; lg[k] = b2.x; lg[k + 1] = b2.y;
+              const float2 a2 = log_exact2(make_float2(clamp_nan(p[k], eps_s, 1000.0f), clamp_nan(p[k + 1], eps_s, 1000.0f)));
+              const float2 b2 = log_exact2(make_float2(clamp_nan(g[k], eps_s, 1000.0f), clamp_nan(g[k + 1], eps_s, 1000.0f)));
+              lp[k] = a2.x; lp[k + 1] = a2.y; lg[k] = b2.x; lg[k + 1] = b2.y;
             }
-        }
-        float out[4];
+          }
+          float out[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < 4; ++k) {
             float gsum = 0.f;
             if constexpr (SI) {
-                const bool m = HAS_MASK ? um[k] : (g[k] > eps_s);
-                if (m && in_range_pos(p[k], eps_s, 1000.0f)) gsum = fmaf(c1, lp[k] - lg[k], c2) * rcp_approx(p[k]);
+              const bool m = HAS_MASK ? um[k] : (g[k] > eps_s);
+              if (m && in_range_pos(p[k], eps_s, 1000.0f)) gsum = fmaf(c1, lp[k] - lg[k], c2) * rcp_approx(p[k]);
             }
             if constexpr (RP) {
-                const bool m = HAS_MASK ? um[k] : (g[k] > eps_r);
-                if (m) {
-                    const float ax = (xf + (float)k) - cxv;            // (float)(x+k) is exact; depth_loss.h:299
-                    float pX, gX, pY, gY;
-                    if (mk_ok) {
-                        pX = div_by_const(__fmul_rn(ax, p[k]), fxe, rfx);
-                        gX = div_by_const(__fmul_rn(ax, g[k]), fxe, rfx);
-                        pY = div_by_const(__fmul_rn(ayv, p[k]), fye, rfy);
-                        gY = div_by_const(__fmul_rn(ayv, g[k]), fye, rfy);
-                    } else {
-                        pX = __fdiv_rn(__fmul_rn(ax, p[k]), fxe);
-                        gX = __fdiv_rn(__fmul_rn(ax, g[k]), fxe);
-                        pY = __fdiv_rn(__fmul_rn(ayv, p[k]), fye);
-                        gY = __fdiv_rn(__fmul_rn(ayv, g[k]), fye);
-                    }
-                    const float dX = pX - gX, dY = pY - gY, dZ = p[k] - g[k];
-                    const float ss = fmaf(dZ, dZ, fmaf(dY, dY, dX * dX)) + eps_r;   // :313-315
-                    const float re = rsqrt_approx(ss);
-                    acc[BF_RP_E] = fmaf(ss, re, acc[BF_RP_E]);
-                    gsum = fmaf(fmaf(dX, ax * rfx, fmaf(dY, yh, dZ)) * re, rpn, gsum);
+              const bool m = HAS_MASK ? um[k] : (g[k] > eps_r);
+              if (m) {
+                const float ax = (xf + (float)k) - cxv;            // (float)(x+k) is exact; depth_loss.h:299
+                float pX, gX, pY, gY;
+                if (mk_ok) {
+                  pX = div_by_const(__fmul_rn(ax, p[k]), fxe, rfx);
+                  gX = div_by_const(__fmul_rn(ax, g[k]), fxe, rfx);
+                  pY = div_by_const(__fmul_rn(ayv, p[k]), fye, rfy);
+                  gY = div_by_const(__fmul_rn(ayv, g[k]), fye, rfy);
+                } else {
+                  pX = __fdiv_rn(__fmul_rn(ax, p[k]), fxe);
+                  gX = __fdiv_rn(__fmul_rn(ax, g[k]), fxe);
+                  pY = __fdiv_rn(__fmul_rn(ayv, p[k]), fye);
+                  gY = __fdiv_rn(__fmul_rn(ayv, g[k]), fye);
                 }
+                const float dX = pX - gX, dY = pY - gY, dZ = p[k] - g[k];
+                const float ss = fmaf(dZ, dZ, fmaf(dY, dY, dX * dX)) + eps_r;   // :313-315
+                const float re = rsqrt_approx(ss);
+                acc[BF_RP_E] = fmaf(ss, re, acc[BF_RP_E]);
+                gsum = fmaf(fmaf(dX, ax * rfx, fmaf(dY, yh, dZ)) * re, rpn, gsum);
+              }
             }
             out[k] = gsum;
+          }
+          if (a.grad) *reinterpret_cast<float4*>(a.grad + off) = make_float4(out[0], out[1], out[2], out[3]);
         }
-        if (a.grad) *reinterpret_cast<float4*>(a.grad + off) = make_float4(out[0], out[1], out[2], out[3]);
       }
     }
     if (publish_partials(a, acc, blockIdx.y * gridDim.x + blockIdx.x, s_f, &s_last)) {

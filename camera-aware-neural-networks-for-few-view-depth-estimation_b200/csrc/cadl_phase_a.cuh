@@ -297,15 +297,16 @@ __global__ void __launch_bounds__(kThreadsA, 4) phase_a_kernel(const PhaseAArgs 
 
     const int nblk = a.B * a.blocks_per_img;
     const volatile double* part = a.a_part;
-    for (int q = 0; q < AF_COUNT; ++q) {
+    // one warp per quantity (fixed lane-strided order + fixed shuffle tree: deterministic), no block barriers
+    for (int q = warp; q < AF_COUNT; q += kThreadsA / 32) {
         if (q == AF_PSUM) continue;
         if (!(F & FA_SI) && (q == AF_SI_S || q == AF_SI_Q)) continue;
         if (!(F & FA_EV) && q >= AF_EV_ABSREL && q <= AF_EV_SUMG) continue;
         if (!(F & FA_TR) && q >= AF_TR_ABSREL && q <= AF_TR_LOGSQ) continue;
         double acc = 0.0;
-        for (int i = tid; i < nblk; i += kThreadsA) acc += part[(size_t)i * AF_COUNT + q];
-        double r = block_sum_double(acc, s_d);
-        if (tid == 0) {
+        for (int i = lane; i < nblk; i += 32) acc += part[(size_t)i * AF_COUNT + q];
+        const double r = warp_sum(acc);
+        if (lane == 0) {
             int st = -1;
             switch (q) {
                 case AF_SI_S: st = ST_SI_S; break;

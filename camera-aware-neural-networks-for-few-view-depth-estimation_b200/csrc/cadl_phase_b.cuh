@@ -124,12 +124,15 @@ __device__ void finalize_results(const PhaseBArgs& a, double* s_d) {
     const int tid = threadIdx.x;
     const volatile double* part = a.b_part;
     __shared__ double s_tot[BF_COUNT];
-    for (int q = 0; q < BF_COUNT; ++q) {
-        if (q == BF_SMX || q == BF_SMY) continue;
-        double acc = 0.0;
-        for (int i = tid; i < a.b_rows; i += blockDim.x) acc += part[(size_t)i * BF_COUNT + q];
-        double r = block_sum_double(acc, s_d);
-        if (tid == 0) s_tot[q] = r;
+    {   // one warp per quantity: fixed lane-strided order + fixed shuffle tree (deterministic), no block barriers
+        const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+        for (int q = warp; q < BF_COUNT; q += nwarp) {
+            if (q == BF_SMX || q == BF_SMY) continue;
+            double acc = 0.0;
+            for (int i = lane; i < a.b_rows; i += 32) acc += part[(size_t)i * BF_COUNT + q];
+            acc = warp_sum(acc);
+            if (lane == 0) s_tot[q] = acc;
+        }
     }
     // smoothness: per-image sums (tiles of an image are contiguous rows), then a_b-weighted total
     double sm_acc = 0.0;

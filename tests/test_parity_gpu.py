@@ -261,6 +261,35 @@ def test_reproj_full_size_config2(pkg, oracle):
     check_grad(g, pr.grad, None, TOL, "config2")
 
 
+def test_config5_shape_reproj_and_metrics(pkg, oracle):
+    """BASELINE config 5 per-GPU shape (B=16, 960x1280: 19.66 M pixels > 2^24): reprojection fwd+bwd with both
+    metric variants fused into the same pass; integer delta counts must be exact where a float mean cannot be."""
+    B, H, W = 16, 960, 1280
+    b = pkg.synth.make_batch(B, H, W, seed=1236)
+    d = _dev()
+    t = {k: v.to(d) for k, v in b.items()}
+    p = pkg.default_params(terms=pkg.TERM_REPROJ, w_reproj=1.0, metrics=pkg.METRICS_EVAL | pkg.METRICS_TRAIN)
+    ws = pkg.stack_fwd_bwd(t["pred"], t["gt"], None, t["K"], None, params=p)
+    torch.cuda.synchronize()
+    r = pkg.results_dict(ws.read_results())
+    pr = t["pred"].clone().requires_grad_(True)
+    loss = oracle.reprojection_loss(pr, t["gt"], t["K"])
+    loss.backward()
+    assert rel_err(r["reproj_loss"], float(loss)) <= TOL
+    check_grad(ws.grad, pr.grad, None, TOL, "config5")
+    ev, evc = oracle.metrics_eval(t["pred"], t["gt"])
+    tr, trc = oracle.metrics_train(t["pred"], t["gt"])
+    assert r["eval_counts"] == evc and r["train_counts"] == trc and evc[0] > 2 ** 23
+    for k in pkg.EVAL_KEYS:
+        if k.startswith("delta") or k == "num_valid_pixels":
+            continue          # the reference's float means of 0/1 over > 2^24 elements are themselves inexact
+        assert rel_err(r["eval"][k], ev[k]) <= TOL, k
+    for k in ("abs_rel", "sq_rel", "rmse", "rmse_log"):
+        assert rel_err(r["train"][k], tr[k]) <= TOL, k
+    # fraction from the exact counts
+    assert abs(r["eval"]["delta_1.25"] - evc[1] / evc[0]) < 1e-6
+
+
 def test_scale_grad(pkg):
     d = _dev()
     g = torch.randn(3, 1, 40, 52, device=d)

@@ -9,6 +9,7 @@
 #include "cadl_phase_a.cuh"
 #include "cadl_phase_b.cuh"
 #include "cadl_phase_b_fast.cuh"
+#include "cadl_phase_b_ws.cuh"
 #include "cadl_rays.cuh"
 #include "cadl_photometric.cuh"
 
@@ -70,7 +71,8 @@ struct Ws {
 
 constexpr int kPointBlocks = 148 * 8;
 int g_force_generic = 0;
-int g_force_no_tma = 0;     // bit 1 of cadl_debug_force_generic: keep the fast kernel but stage with cp.async   // cadl_debug_force_generic(): tests compare the two phase-B kernels
+int g_force_no_tma = 0;
+int g_use_ws = 0;           // bit 2: warp-specialised persistent kernel instead of the plain one-tile-per-CTA fast kernel     // bit 1 of cadl_debug_force_generic: keep the fast kernel but stage with cp.async   // cadl_debug_force_generic(): tests compare the two phase-B kernels
 
 WsLayout layout_for(int B, int H, int W) {
     WsLayout L = ws_layout(B, H, W);
@@ -182,6 +184,26 @@ cudaError_t launch_fast_m(PhaseBArgs& a, cudaStream_t st) {
             tm.pp = a.pred; tm.pg = a.gt; tm.B = a.B; tm.H = a.H; tm.W = a.W;
         }
         a.use_tma = tm.ok ? 1 : 0;
+    }
+    if constexpr ((F & FB_GRAD) != 0) {
+        if (a.use_tma && g_use_ws) {
+            // warp-specialised persistent form (opt-in: measured 198 us vs 194 us for the plain kernel at config 3 --
+            // both are bound by warps per SM, i.e. by the 128 registers of the full-resolution pass)
+            static bool ws_configured = false;
+            static int num_sms = 0;
+            if (!ws_configured) {
+                cudaError_t e = cudaFuncSetAttribute(phase_b_ws_kernel<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)kWsSmemBytes);
+                if (e != cudaSuccess) return e;
+                int dev = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+                ws_configured = true;
+            }
+            const int grid = a.b_rows < num_sms ? a.b_rows : num_sms;
+            phase_b_ws_kernel<F, M><<<grid, kWsThreads, kWsSmemBytes, st>>>(a, g_maps.pred, g_maps.gt);
+            return cudaGetLastError();
+        }
     }
     phase_b_fast_kernel<F, M><<<a.b_rows, kThreadsB, kFastSmemBytes, st>>>(a, g_maps.pred, g_maps.gt);
     return cudaGetLastError();
@@ -360,7 +382,11 @@ void cadl_default_params(cadl_params* p) {
 }
 
 int cadl_version(void) { return CADL_VERSION; }
-void cadl_debug_force_generic(int on) { g_force_generic = on & 1; g_force_no_tma = (on >> 1) & 1; }
+void cadl_debug_force_generic(int on) {
+    g_force_generic = on & 1;
+    g_force_no_tma = (on >> 1) & 1;
+    g_use_ws = (on >> 2) & 1;
+}
 size_t cadl_sizeof_params(void) { return sizeof(cadl_params); }
 size_t cadl_sizeof_results(void) { return sizeof(cadl_results); }
 

@@ -169,7 +169,6 @@ __global__ void __launch_bounds__(kThreadsA, 4) phase_a_kernel(const PhaseAArgs 
     constexpr bool NEED_P = (F & (FA_SI | FA_PSUM | FA_EV | FA_TR)) != 0;
     constexpr bool NEED_G = (F & (FA_SI | FA_RP | FA_EV | FA_TR)) != 0;
     __shared__ float s_f[kThreadsA / 32][AF_COUNT];
-    __shared__ double s_d[8];
     __shared__ int s_last;
     __shared__ float s_to[kToSlots * kThreadsA];
     __shared__ unsigned s_iw[kThreadsA / 32][AI_COUNT];

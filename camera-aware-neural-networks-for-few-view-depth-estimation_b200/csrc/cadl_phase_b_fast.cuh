@@ -170,203 +170,145 @@ __device__ __forceinline__ void coef_pass(const PhaseBArgs& a, const FastSmem& s
     acc_y += ay;
 }
 
-template <int F, bool HAS_MASK>
-__global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseBArgs a,
-                                                                    const __grid_constant__ CUtensorMap tm_pred,
-                                                                    const __grid_constant__ CUtensorMap tm_gt) {
-    extern __shared__ __align__(128) float smem_raw[];
-    __shared__ __align__(8) unsigned long long s_bar;
-    __shared__ float s_f[kThreadsB / 32][BF_COUNT];
-    __shared__ double s_d[8];
-    __shared__ float s_c[8];
-    __shared__ int s_last;
-    FastSmem sm;
-    sm.sp = smem_raw;
-    sm.sg = sm.sp + FRH * FRW;
-    sm.pl = sm.sg + FRH * FRW;
-    sm.pg = sm.pl + kFPoolCells;
-    sm.cc = sm.pg + kFPoolCells;
+// Thread-group barrier: the whole CTA (BAR == 0) or a named barrier over kThreadsB threads (warp-specialised kernel)
+template <int BAR>
+__device__ __forceinline__ void gsync() {
+    if constexpr (BAR == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" :: "n"(BAR), "n"(kThreadsB) : "memory");
+}
 
+// Everything between "the raw pred/gt tile is in shared memory" and the full-resolution pass: border ring,
+// avg-pool pyramid, pooled logs, per-cell coefficients of the three coarse scales, logs in place.
+// Executed by a group of kThreadsB threads (tid = index inside the group).
+template <int BAR>
+__device__ __forceinline__ void fast_prelude(const PhaseBArgs& a, const FastSmem& sm, int tid, int y0, int x0,
+                                             bool zero_filled, float (&acc)[BF_COUNT]) {
+    const int H = a.H, W = a.W;
+    if (zero_filled) {   // TMA staging: patch the replicated 1-pixel ring of border tiles
+        const int r_top = (y0 == 0) ? HALO - 1 : -1;                       // staged row of image row -1
+        const int r_bot = (H - y0 + HALO < FRH) ? H - y0 + HALO : -1;      // staged row of image row H
+        const int c_lft = (x0 == 0) ? HALO - 1 : -1;
+        const int c_rgt = (W - x0 + HALO < FRW) ? W - x0 + HALO : -1;
+        if (r_top >= 0 || r_bot >= 0 || c_lft >= 0 || c_rgt >= 0) {       // block-uniform: the tile touches the border
+            if (r_top >= 0 && tid < FRW) { sm.sp[r_top * FRW + tid] = sm.sp[(r_top + 1) * FRW + tid]; sm.sg[r_top * FRW + tid] = sm.sg[(r_top + 1) * FRW + tid]; }
+            if (r_bot >= 0 && tid < FRW) { sm.sp[r_bot * FRW + tid] = sm.sp[(r_bot - 1) * FRW + tid]; sm.sg[r_bot * FRW + tid] = sm.sg[(r_bot - 1) * FRW + tid]; }
+            gsync<BAR>();                                               // rows first, then columns (corners follow)
+            if (c_lft >= 0 && tid < FRH) { sm.sp[tid * FRW + c_lft] = sm.sp[tid * FRW + c_lft + 1]; sm.sg[tid * FRW + c_lft] = sm.sg[tid * FRW + c_lft + 1]; }
+            if (c_rgt >= 0 && tid < FRH) { sm.sp[tid * FRW + c_rgt] = sm.sp[tid * FRW + c_rgt - 1]; sm.sg[tid * FRW + c_rgt] = sm.sg[tid * FRW + c_rgt - 1]; }
+        }
+    }
+    gsync<BAR>();
+
+    // ---------------- P2: avg-pool pyramid in the reference's summation order, pooled logs ----------------
+    {
+        constexpr int BR = FRH / 8, BC = FRW / 8;   // 8 x 18 blocks of 8x8
+        // items 0..191: interior blocks (6 x 16 per tensor) -- six whole warps on the unconditional path;
+        // items 192..287: the ring of halo blocks (48 per tensor)
+        constexpr int NI = (BR - 2) * (BC - 2), NH = BR * BC - NI;
+        for (int item = tid; item < 2 * BR * BC; item += kThreadsB) {
+            int t, by, bx;
+            if (item < 2 * NI) {
+                t = item >= NI ? 1 : 0;
+                const int idx = item - t * NI;
+                by = 1 + idx / (BC - 2);
+                bx = 1 + idx - (by - 1) * (BC - 2);
+            } else {
+                const int h = item - 2 * NI;
+                t = h >= NH ? 1 : 0;
+                const int idx = h - t * NH;
+                if (idx < BC) { by = 0; bx = idx; }
+                else if (idx < 2 * BC) { by = BR - 1; bx = idx - BC; }
+                else if (idx < 2 * BC + (BR - 2)) { by = 1 + idx - 2 * BC; bx = 0; }
+                else { by = 1 + idx - 2 * BC - (BR - 2); bx = BC - 1; }
+            }
+            float* dst = (t == 0 ? sm.pl : sm.pg);
+            // H, W and the block origin are multiples of 8: a block is entirely inside or outside the image
+            const int gby = y0 - HALO + 8 * by, gbx = x0 - HALO + 8 * bx;
+            const bool valid = gby >= 0 && gby < H && gbx >= 0 && gbx < W;
+            const bool interior = by >= 1 && by <= BR - 2 && bx >= 1 && bx <= BC - 2;
+            if (!valid) {   // cells outside the image: defined but inert (1/q = 0; logs patched by pooled_replicate)
+#pragma unroll
+                for (int S = 1; S <= 3; ++S) {
+                    const int nc = 8 >> S, cy0 = by * nc - nc, cx0 = bx * nc - nc;
+                    for (int ci = 0; ci < nc; ++ci)
+                        for (int cj = 0; cj < nc; ++cj) {
+                            const int cy = cy0 + ci, cx = cx0 + cj;
+                            if (cy < -1 || cy > (FTH >> S) || cx < -1 || cx > (FTW >> S)) continue;
+                            dst[fpool_off(S) + (cy + 1) * fpool_w(S) + (cx + 1)] = 0.f;
+                            if (t == 0 && cy >= 0 && cy < (FTH >> S) && cx >= 0 && cx < (FTW >> S))
+                                sm.cc[fcc_off(S) + cy * fcc_w(S) + cx] = 0.f;
+                        }
+                }
+                continue;
+            }
+            const float* src = (t == 0 ? sm.sp : sm.sg) + (by * 8) * FRW + bx * 8;
+            float v[8][8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const float4 lo = *reinterpret_cast<const float4*>(src + r * FRW);
+                const float4 hi = *reinterpret_cast<const float4*>(src + r * FRW + 4);
+                v[r][0] = lo.x; v[r][1] = lo.y; v[r][2] = lo.z; v[r][3] = lo.w;
+                v[r][4] = hi.x; v[r][5] = hi.y; v[r][6] = hi.z; v[r][7] = hi.w;
+            }
+            if (interior) {
+                pool_scale<1, true>(v, a.eps_grad, sm.cc, dst, t, by, bx);
+                pool_scale<2, true>(v, a.eps_grad, sm.cc, dst, t, by, bx);
+                pool_scale<3, true>(v, a.eps_grad, sm.cc, dst, t, by, bx);
+            } else {
+                pool_scale<1, false>(v, a.eps_grad, sm.cc, dst, t, by, bx);
+                pool_scale<2, false>(v, a.eps_grad, sm.cc, dst, t, by, bx);
+                pool_scale<3, false>(v, a.eps_grad, sm.cc, dst, t, by, bx);
+            }
+        }
+    }
+    gsync<BAR>();
+    if (y0 == 0 || x0 == 0 || H - y0 <= FTH || W - x0 <= FTW) {   // block-uniform: the tile touches the image border
+        pooled_replicate<1>(a, sm, tid, y0, x0, true);
+        pooled_replicate<2>(a, sm, tid, y0, x0, true);
+        pooled_replicate<3>(a, sm, tid, y0, x0, true);
+        gsync<BAR>();
+        pooled_replicate<1>(a, sm, tid, y0, x0, false);
+        pooled_replicate<2>(a, sm, tid, y0, x0, false);
+        pooled_replicate<3>(a, sm, tid, y0, x0, false);
+        gsync<BAR>();
+    }
+
+    // ---------------- P3a: coefficients of scales 3 and 2 ----------------
+    const float wg = 0.25f * a.w_grad * a.upstream;      // 1/num_scales * weight * upstream
+    coef_pass<3, false>(a, sm, tid, y0, x0, wg * (1.0f / 64.0f), acc[BF_GX3], acc[BF_GY3]);
+    coef_pass<2, false>(a, sm, tid, y0, x0, wg * (1.0f / 16.0f), acc[BF_GX2], acc[BF_GY2]);
+    // ---------------- P3b: logs of the (FTH+2) x (FTW+2) ring + interior, in place, 2 px per step ----------------
+    {
+        constexpr int LR = FTH + 2, LC2 = (FTW + 2) / 2;   // 50 rows x 65 pairs
+        for (int i = tid; i < LR * LC2; i += kThreadsB) {
+            const int rr = i / LC2, cp = i - rr * LC2;
+            const int o = (rr + HALO - 1) * FRW + (HALO - 1) + 2 * cp;
+            const float2 pv = make_float2(clamp_nan(sm.sp[o], a.eps_grad, 1000.0f), clamp_nan(sm.sp[o + 1], a.eps_grad, 1000.0f));
+            const float2 gv = make_float2(clamp_nan(sm.sg[o], a.eps_grad, 1000.0f), clamp_nan(sm.sg[o + 1], a.eps_grad, 1000.0f));
+            const float2 lpv = log_exact2(pv), lgv = log_exact2(gv);        // depth_loss.h:115-116
+            sm.sp[o] = lpv.x; sm.sp[o + 1] = lpv.y;
+            sm.sg[o] = lgv.x; sm.sg[o + 1] = lgv.y;
+        }
+    }
+    gsync<BAR>();
+    // ---------------- P3c: scale 1 + the two coarser gathered: what each pixel adds ----------------
+    coef_pass<1, true>(a, sm, tid, y0, x0, wg * 0.25f, acc[BF_GX1], acc[BF_GY1]);
+}
+
+// The full-resolution pass over one staged tile, executed by 8 warps (warp = index inside the group).
+template <int F, bool HAS_MASK>
+__device__ __forceinline__ void fast_p4(const PhaseBArgs& a, const FastSmem& sm, int warp, int lane, int b, int y0, int x0,
+                                        const float* s_c, float (&acc)[BF_COUNT]) {
     constexpr bool GRAD = (F & FB_GRAD) != 0;
     constexpr bool SMOOTH = (F & FB_SMOOTH) != 0;
     constexpr bool SI = (F & FB_SI) != 0;
     constexpr bool RP = (F & FB_RP) != 0;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.x;
-    const int tx = tile % a.tiles_x;
-    const int ty = (tile / a.tiles_x) % a.tiles_y;
-    const int b = tile / (a.tiles_x * a.tiles_y);
-    const int x0 = tx * FTW, y0 = ty * FTH;
     const int H = a.H, W = a.W;
     const int img = b * H * W;                               // B*H*W < 2^31 (checked on the host)
     const float* __restrict__ predb = a.pred + img;
     const float* __restrict__ gtb = a.gt ? a.gt + img : nullptr;
     const float up = a.upstream;
-
-    // Scalars every pixel needs, derived once per CTA from the phase-A statistics (SURVEY 8a a1, a3, a4);
-    // weights and the upstream gradient are folded in here so the pixel loop has no extra multiplies.
-    if (tid == 0) {
-        const double n = a.stats[ST_SI_N], S = a.stats[ST_SI_S], nr = a.stats[ST_RP_N];
-        s_c[0] = n > 0.0 ? (float)(2.0 / n) * a.w_si * up : 0.f;                                   // c1
-        s_c[1] = n > 0.0 ? (float)(-2.0 * (double)a.lambda * S / (n * n)) * a.w_si * up : 0.f;     // c2
-        s_c[2] = nr > 0.0 ? (float)(1.0 / nr) * a.w_rp * up : 0.f;                                 // 1/n (reprojection)
-        s_c[3] = SMOOTH ? (1.0f / ((float)(a.img_psum[b] / ((double)H * W)) + a.eps_smooth)) * a.w_smooth * up : 0.f;  // a_b (:192-193)
-    }
-
-    float acc[BF_COUNT];
-#pragma unroll
-    for (int q = 0; q < BF_COUNT; ++q) acc[q] = 0.f;
-
-    if constexpr (GRAD) {
-        // ---------------- P1: stage raw pred / gt with an 8-pixel halo ----------------
-        if (a.use_tma) {
-            // TMA: one thread issues two 3-D box loads (144 x 64 x 1 floats each); pixels outside the image
-            // arrive as zeros.  Only the 1-pixel ring around the image needs the replicated border value
-            // (pooled cells outside the image are invalid anyway), so border tiles patch one row / column.
-            if (tid == 0) mbar_init(&s_bar, 1);
-            __syncthreads();
-            if (tid == 0) {
-                mbar_expect_tx(&s_bar, 2u * FRH * FRW * sizeof(float));
-                tma_load_3d(sm.sp, &tm_pred, x0 - HALO, y0 - HALO, b, &s_bar);
-                tma_load_3d(sm.sg, &tm_gt, x0 - HALO, y0 - HALO, b, &s_bar);
-            }
-            mbar_wait(&s_bar, 0);
-            const int r_top = (y0 == 0) ? HALO - 1 : -1;                       // staged row of image row -1
-            const int r_bot = (H - y0 + HALO < FRH) ? H - y0 + HALO : -1;      // staged row of image row H
-            const int c_lft = (x0 == 0) ? HALO - 1 : -1;
-            const int c_rgt = (W - x0 + HALO < FRW) ? W - x0 + HALO : -1;
-            if (r_top >= 0 || r_bot >= 0 || c_lft >= 0 || c_rgt >= 0) {       // block-uniform: the tile touches the border
-                if (r_top >= 0 && tid < FRW) { sm.sp[r_top * FRW + tid] = sm.sp[(r_top + 1) * FRW + tid]; sm.sg[r_top * FRW + tid] = sm.sg[(r_top + 1) * FRW + tid]; }
-                if (r_bot >= 0 && tid < FRW) { sm.sp[r_bot * FRW + tid] = sm.sp[(r_bot - 1) * FRW + tid]; sm.sg[r_bot * FRW + tid] = sm.sg[(r_bot - 1) * FRW + tid]; }
-                __syncthreads();                                               // rows first, then columns (corners follow)
-                if (c_lft >= 0 && tid < FRH) { sm.sp[tid * FRW + c_lft] = sm.sp[tid * FRW + c_lft + 1]; sm.sg[tid * FRW + c_lft] = sm.sg[tid * FRW + c_lft + 1]; }
-                if (c_rgt >= 0 && tid < FRH) { sm.sp[tid * FRW + c_rgt] = sm.sp[tid * FRW + c_rgt - 1]; sm.sg[tid * FRW + c_rgt] = sm.sg[tid * FRW + c_rgt - 1]; }
-            }
-        } else {
-            // cp.async fallback (no tensor maps): 16-byte copies, border pixels replicated
-            for (int rr = warp; rr < FRH; rr += kThreadsB / 32) {
-                const int rowo = clampi(y0 - HALO + rr, 0, H - 1) * W;
-#pragma unroll
-                for (int pass = 0; pass < 2; ++pass) {
-                    const int c4 = pass * 32 + lane;
-                    if (c4 < FRW / 4) {
-                        const int gx = x0 - HALO + 4 * c4;
-                        float* dp = sm.sp + rr * FRW + 4 * c4;
-                        float* dg = sm.sg + rr * FRW + 4 * c4;
-                        if (gx >= 0 && gx + 3 < W) {
-                            cp_async16(dp, predb + rowo + gx);
-                            cp_async16(dg, gtb + rowo + gx);
-                        } else {   // whole float4 outside (W % 4 == 0): replicate the border pixel
-                            const int cx = gx < 0 ? 0 : W - 1;
-                            const float ps = __ldg(predb + rowo + cx), gs = __ldg(gtb + rowo + cx);
-                            *reinterpret_cast<float4*>(dp) = make_float4(ps, ps, ps, ps);
-                            *reinterpret_cast<float4*>(dg) = make_float4(gs, gs, gs, gs);
-                        }
-                    }
-                }
-            }
-            cp_async_wait_all();
-        }
-        __syncthreads();
-
-        // ---------------- P2: avg-pool pyramid in the reference's summation order, pooled logs ----------------
-        {
-            constexpr int BR = FRH / 8, BC = FRW / 8;   // 8 x 18 blocks of 8x8
-            // items 0..191: interior blocks (6 x 16 per tensor) -- six whole warps on the unconditional path;
-            // items 192..287: the ring of halo blocks (48 per tensor)
-            constexpr int NI = (BR - 2) * (BC - 2), NH = BR * BC - NI;
-            for (int item = tid; item < 2 * BR * BC; item += kThreadsB) {
-                int t, by, bx;
-                if (item < 2 * NI) {
-                    t = item >= NI ? 1 : 0;
-                    const int idx = item - t * NI;
-                    by = 1 + idx / (BC - 2);
-                    bx = 1 + idx - (by - 1) * (BC - 2);
-                } else {
-                    const int h = item - 2 * NI;
-                    t = h >= NH ? 1 : 0;
-                    const int idx = h - t * NH;
-                    if (idx < BC) { by = 0; bx = idx; }
-                    else if (idx < 2 * BC) { by = BR - 1; bx = idx - BC; }
-                    else if (idx < 2 * BC + (BR - 2)) { by = 1 + idx - 2 * BC; bx = 0; }
-                    else { by = 1 + idx - 2 * BC - (BR - 2); bx = BC - 1; }
-                }
-                float* dst = (t == 0 ? sm.pl : sm.pg);
-                // H, W and the block origin are multiples of 8: a block is entirely inside or outside the image
-                const int gby = y0 - HALO + 8 * by, gbx = x0 - HALO + 8 * bx;
-                const bool valid = gby >= 0 && gby < H && gbx >= 0 && gbx < W;
-                const bool interior = by >= 1 && by <= BR - 2 && bx >= 1 && bx <= BC - 2;
-                if (!valid) {   // cells outside the image: defined but inert (1/q = 0; logs patched by pooled_replicate)
-#pragma unroll
-                    for (int S = 1; S <= 3; ++S) {
-                        const int nc = 8 >> S, cy0 = by * nc - nc, cx0 = bx * nc - nc;
-                        for (int ci = 0; ci < nc; ++ci)
-                            for (int cj = 0; cj < nc; ++cj) {
-                                const int cy = cy0 + ci, cx = cx0 + cj;
-                                if (cy < -1 || cy > (FTH >> S) || cx < -1 || cx > (FTW >> S)) continue;
-                                dst[fpool_off(S) + (cy + 1) * fpool_w(S) + (cx + 1)] = 0.f;
-                                if (t == 0 && cy >= 0 && cy < (FTH >> S) && cx >= 0 && cx < (FTW >> S))
-                                    sm.cc[fcc_off(S) + cy * fcc_w(S) + cx] = 0.f;
-                            }
-                    }
-                    continue;
-                }
-                const float* src = (t == 0 ? sm.sp : sm.sg) + (by * 8) * FRW + bx * 8;
-                float v[8][8];
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const float4 lo = *reinterpret_cast<const float4*>(src + r * FRW);
-                    const float4 hi = *reinterpret_cast<const float4*>(src + r * FRW + 4);
-                    v[r][0] = lo.x; v[r][1] = lo.y; v[r][2] = lo.z; v[r][3] = lo.w;
-                    v[r][4] = hi.x; v[r][5] = hi.y; v[r][6] = hi.z; v[r][7] = hi.w;
-                }
-                if (interior) {
-                    pool_scale<1, true>(v, a.eps_grad, sm.cc, dst, t, by, bx);
-                    pool_scale<2, true>(v, a.eps_grad, sm.cc, dst, t, by, bx);
-                    pool_scale<3, true>(v, a.eps_grad, sm.cc, dst, t, by, bx);
-                } else {
-                    pool_scale<1, false>(v, a.eps_grad, sm.cc, dst, t, by, bx);
-                    pool_scale<2, false>(v, a.eps_grad, sm.cc, dst, t, by, bx);
-                    pool_scale<3, false>(v, a.eps_grad, sm.cc, dst, t, by, bx);
-                }
-            }
-        }
-        __syncthreads();
-        if (y0 == 0 || x0 == 0 || H - y0 <= FTH || W - x0 <= FTW) {   // block-uniform: the tile touches the image border
-            pooled_replicate<1>(a, sm, tid, y0, x0, true);
-            pooled_replicate<2>(a, sm, tid, y0, x0, true);
-            pooled_replicate<3>(a, sm, tid, y0, x0, true);
-            __syncthreads();
-            pooled_replicate<1>(a, sm, tid, y0, x0, false);
-            pooled_replicate<2>(a, sm, tid, y0, x0, false);
-            pooled_replicate<3>(a, sm, tid, y0, x0, false);
-            __syncthreads();
-        }
-
-        // ---------------- P3a: coefficients of scales 3 and 2 ----------------
-        const float wg = 0.25f * a.w_grad * up;              // 1/num_scales * weight * upstream
-        coef_pass<3, false>(a, sm, tid, y0, x0, wg * (1.0f / 64.0f), acc[BF_GX3], acc[BF_GY3]);
-        coef_pass<2, false>(a, sm, tid, y0, x0, wg * (1.0f / 16.0f), acc[BF_GX2], acc[BF_GY2]);
-        // ---------------- P3b: logs of the (FTH+2) x (FTW+2) ring + interior, in place, 2 px per step ----------------
-        {
-            constexpr int LR = FTH + 2, LC2 = (FTW + 2) / 2;   // 50 rows x 65 pairs
-            for (int i = tid; i < LR * LC2; i += kThreadsB) {
-                const int rr = i / LC2, cp = i - rr * LC2;
-                const int o = (rr + HALO - 1) * FRW + (HALO - 1) + 2 * cp;
-                const float2 pv = make_float2(clamp_nan(sm.sp[o], a.eps_grad, 1000.0f), clamp_nan(sm.sp[o + 1], a.eps_grad, 1000.0f));
-                const float2 gv = make_float2(clamp_nan(sm.sg[o], a.eps_grad, 1000.0f), clamp_nan(sm.sg[o + 1], a.eps_grad, 1000.0f));
-                const float2 lpv = log_exact2(pv), lgv = log_exact2(gv);        // depth_loss.h:115-116
-                sm.sp[o] = lpv.x; sm.sp[o + 1] = lpv.y;
-                sm.sg[o] = lgv.x; sm.sg[o + 1] = lgv.y;
-            }
-        }
-        __syncthreads();
-        // ---------------- P3c: scale 1 + the two coarser gathered: what each pixel adds ----------------
-        coef_pass<1, true>(a, sm, tid, y0, x0, wg * 0.25f, acc[BF_GX1], acc[BF_GY1]);
-    }
-    __syncthreads();
-
+    // one warp = 128 columns, marching down FRPW rows; see file header
     // ---------------- P4: full-resolution pass.  One warp = 128 columns, marching down FRPW rows ----------------
     {
         const int xl = 4 * lane;
@@ -648,6 +590,98 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
                 for (int k = 0; k < 5; ++k) Ic[c][k] = In[c][k];
         }
     }
+
+}
+
+template <int F, bool HAS_MASK>
+__global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseBArgs a,
+                                                                    const __grid_constant__ CUtensorMap tm_pred,
+                                                                    const __grid_constant__ CUtensorMap tm_gt) {
+    extern __shared__ __align__(128) float smem_raw[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ float s_f[kThreadsB / 32][BF_COUNT];
+    __shared__ double s_d[8];
+    __shared__ float s_c[8];
+    __shared__ int s_last;
+    FastSmem sm;
+    sm.sp = smem_raw;
+    sm.sg = sm.sp + FRH * FRW;
+    sm.pl = sm.sg + FRH * FRW;
+    sm.pg = sm.pl + kFPoolCells;
+    sm.cc = sm.pg + kFPoolCells;
+
+    constexpr bool GRAD = (F & FB_GRAD) != 0;
+    constexpr bool SMOOTH = (F & FB_SMOOTH) != 0;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x;
+    const int tx = tile % a.tiles_x;
+    const int ty = (tile / a.tiles_x) % a.tiles_y;
+    const int b = tile / (a.tiles_x * a.tiles_y);
+    const int x0 = tx * FTW, y0 = ty * FTH;
+    const int H = a.H, W = a.W;
+    const int img = b * H * W;                               // B*H*W < 2^31 (checked on the host)
+    const float* __restrict__ predb = a.pred + img;
+    const float* __restrict__ gtb = a.gt ? a.gt + img : nullptr;
+    const float up = a.upstream;
+
+    // Scalars every pixel needs, derived once per CTA from the phase-A statistics (SURVEY 8a a1, a3, a4);
+    // weights and the upstream gradient are folded in here so the pixel loop has no extra multiplies.
+    if (tid == 0) {
+        const double n = a.stats[ST_SI_N], S = a.stats[ST_SI_S], nr = a.stats[ST_RP_N];
+        s_c[0] = n > 0.0 ? (float)(2.0 / n) * a.w_si * up : 0.f;                                   // c1
+        s_c[1] = n > 0.0 ? (float)(-2.0 * (double)a.lambda * S / (n * n)) * a.w_si * up : 0.f;     // c2
+        s_c[2] = nr > 0.0 ? (float)(1.0 / nr) * a.w_rp * up : 0.f;                                 // 1/n (reprojection)
+        s_c[3] = SMOOTH ? (1.0f / ((float)(a.img_psum[b] / ((double)H * W)) + a.eps_smooth)) * a.w_smooth * up : 0.f;  // a_b (:192-193)
+    }
+
+    float acc[BF_COUNT];
+#pragma unroll
+    for (int q = 0; q < BF_COUNT; ++q) acc[q] = 0.f;
+
+    if constexpr (GRAD) {
+        // ---------------- P1: stage raw pred / gt with an 8-pixel halo ----------------
+        if (a.use_tma) {
+            // TMA: one thread issues two 3-D box loads (144 x 64 x 1 floats each); pixels outside the image
+            // arrive as zeros.  Only the 1-pixel ring around the image needs the replicated border value
+            // (pooled cells outside the image are invalid anyway), so border tiles patch one row / column.
+            if (tid == 0) mbar_init(&s_bar, 1);
+            __syncthreads();
+            if (tid == 0) {
+                mbar_expect_tx(&s_bar, 2u * FRH * FRW * sizeof(float));
+                tma_load_3d(sm.sp, &tm_pred, x0 - HALO, y0 - HALO, b, &s_bar);
+                tma_load_3d(sm.sg, &tm_gt, x0 - HALO, y0 - HALO, b, &s_bar);
+            }
+            mbar_wait(&s_bar, 0);
+        } else {
+            // cp.async fallback (no tensor maps): 16-byte copies, border pixels replicated
+            for (int rr = warp; rr < FRH; rr += kThreadsB / 32) {
+                const int rowo = clampi(y0 - HALO + rr, 0, H - 1) * W;
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int c4 = pass * 32 + lane;
+                    if (c4 < FRW / 4) {
+                        const int gx = x0 - HALO + 4 * c4;
+                        float* dp = sm.sp + rr * FRW + 4 * c4;
+                        float* dg = sm.sg + rr * FRW + 4 * c4;
+                        if (gx >= 0 && gx + 3 < W) {
+                            cp_async16(dp, predb + rowo + gx);
+                            cp_async16(dg, gtb + rowo + gx);
+                        } else {   // whole float4 outside (W % 4 == 0): replicate the border pixel
+                            const int cx = gx < 0 ? 0 : W - 1;
+                            const float ps = __ldg(predb + rowo + cx), gs = __ldg(gtb + rowo + cx);
+                            *reinterpret_cast<float4*>(dp) = make_float4(ps, ps, ps, ps);
+                            *reinterpret_cast<float4*>(dg) = make_float4(gs, gs, gs, gs);
+                        }
+                    }
+                }
+            }
+            cp_async_wait_all();
+        }
+        fast_prelude<0>(a, sm, tid, y0, x0, a.use_tma != 0, acc);
+    }
+    __syncthreads();
+    fast_p4<F, HAS_MASK>(a, sm, warp, lane, b, y0, x0, s_c, acc);
 
     if (publish_partials(a, acc, tile, s_f, &s_last)) {
         finalize_results(a, s_d);

@@ -63,6 +63,7 @@ ABI_SYMBOLS = (
     "cadl_stack_fwd_bwd", "cadl_stack_reduce", "cadl_stack_grad", "cadl_stats_offset", "cadl_stats_count",
     "cadl_si_fwd_bwd", "cadl_gradmatch_fwd_bwd", "cadl_smooth_fwd_bwd", "cadl_reproj_fwd_bwd",
     "cadl_scale_grad", "cadl_metrics", "cadl_rays_from_K", "cadl_photometric_fwd_bwd",
+    "cadl_batch_prep", "cadl_clip_workspace_bytes", "cadl_clip_grad_norm",
 )
 
 _lib = None
@@ -110,6 +111,9 @@ def lib() -> C.CDLL:
     L.cadl_rays_from_K.argtypes = [f32p, C.c_int, f32p, C.c_int, C.c_int, C.c_int, C.c_int, f32p, vp]
     L.cadl_photometric_fwd_bwd.argtypes = [f32p, f32p, C.c_int, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int,
                                            C.c_float, C.c_float, f32p, vp, vp, C.c_size_t, vp]
+    L.cadl_batch_prep.argtypes = [f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, vp]
+    L.cadl_clip_workspace_bytes.restype = C.c_size_t
+    L.cadl_clip_grad_norm.argtypes = [vp, vp, vp, C.c_int, C.c_longlong, C.c_float, f32p, vp, C.c_size_t, C.c_int, vp]
     L.cadl_debug_force_generic.argtypes = [C.c_int]
     L.cadl_debug_force_generic.restype = None
     L.cadl_selftest.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_float, vp, vp]
@@ -291,6 +295,53 @@ def photometric_fwd_bwd(pred, K, T, source, target, eps: float = 1e-6, upstream:
                                             _stream(pred))
     _check(rc, "cadl_photometric_fwd_bwd")
     return ws
+
+
+def batch_prep(rgb, depth, K, H: int, W: int):
+    """SunRGBDLoader::resizeSample on the device: (rgb bilinear, depth nearest, K rescaled) -> (B,.,H,W)."""
+    _require_cuda(rgb, depth, K)
+    B, _, h, w = rgb.shape
+    rgb_o = torch.empty(B, 3, H, W, dtype=torch.float32, device=rgb.device)
+    dep_o = torch.empty(B, 1, H, W, dtype=torch.float32, device=rgb.device)
+    K_o = torch.empty(B, 3, 3, dtype=torch.float32, device=rgb.device)
+    with torch.cuda.device(rgb.device):
+        rc = lib().cadl_batch_prep(_ptr(rgb), _ptr(depth), _ptr(K), B, h, w, H, W, _ptr(rgb_o), _ptr(dep_o), _ptr(K_o),
+                                   _stream(rgb))
+    _check(rc, "cadl_batch_prep")
+    return rgb_o, dep_o, K_o
+
+
+class GradClipper:
+    """clip_grad_norm_ over a fixed list of gradient tensors, no host sync: the device arrays of pointers and
+    sizes are built once (per model), each call is two launches; total norm and coefficient stay on the device."""
+
+    CHUNK = 4096
+
+    def __init__(self, grads):
+        grads = [g for g in grads if g is not None]
+        assert grads and all(g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() for g in grads)
+        self.grads = grads
+        dev = grads[0].device
+        sizes = [g.numel() for g in grads]
+        prefix = [0]
+        for n in sizes:
+            prefix.append(prefix[-1] + (n + self.CHUNK - 1) // self.CHUNK)
+        self.total_chunks = prefix[-1]
+        self.ptrs = torch.tensor([g.data_ptr() for g in grads], dtype=torch.int64, device=dev)
+        self.sizes = torch.tensor(sizes, dtype=torch.int64, device=dev)
+        self.prefix = torch.tensor(prefix, dtype=torch.int64, device=dev)
+        self.out = torch.zeros(2, dtype=torch.float32, device=dev)          # total norm, clip coefficient
+        self.ws_bytes = int(lib().cadl_clip_workspace_bytes())
+        self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=dev)
+
+    def __call__(self, max_norm: float, clip: bool = True) -> torch.Tensor:
+        dev = self.out.device
+        with torch.cuda.device(dev):
+            rc = lib().cadl_clip_grad_norm(_ptr(self.ptrs), _ptr(self.sizes), _ptr(self.prefix), len(self.grads),
+                                           self.total_chunks, float(max_norm), _ptr(self.out), _ptr(self.ws), self.ws_bytes,
+                                           1 if clip else 0, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _check(rc, "cadl_clip_grad_norm")
+        return self.out
 
 
 from .harness import StepHarness, StepCfg  # noqa: E402

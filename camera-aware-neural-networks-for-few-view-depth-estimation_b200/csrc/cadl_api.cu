@@ -12,6 +12,7 @@
 #include "cadl_phase_b_ws.cuh"
 #include "cadl_rays.cuh"
 #include "cadl_photometric.cuh"
+#include "cadl_next.cuh"
 
 using namespace cadl;
 
@@ -555,6 +556,38 @@ int cadl_rays_from_K(const float* K, int k_batched, const float* pose, int B, in
     if (!K || !out) return CADL_ERR_NULL;
     if (B < 1 || H < 1 || W < 1 || (layout != 0 && layout != 1)) return CADL_ERR_SHAPE;
     return cuda_rc(launch_rays(K, k_batched, pose, B, H, W, layout, out, (cudaStream_t)stream));
+}
+
+int cadl_batch_prep(const float* rgb_in, const float* depth_in, const float* K_in, int B, int h, int w, int H, int W,
+                    float* rgb_out, float* depth_out, float* K_out, cadl_stream_t stream) {
+    if (!rgb_in || !depth_in || !K_in || !rgb_out || !depth_out || !K_out) return CADL_ERR_NULL;
+    if (B < 1 || h < 1 || w < 1 || H < 1 || W < 1 || H > 65535 || B > 65535) return CADL_ERR_SHAPE;
+    PrepArgs a{rgb_in, depth_in, K_in, rgb_out, depth_out, K_out, B, h, w, H, W};
+    return cuda_rc(launch_batch_prep(a, (cudaStream_t)stream));
+}
+
+size_t cadl_clip_workspace_bytes(void) { return 256 + sizeof(double) * 148 * 8; }
+
+int cadl_clip_grad_norm(float* const* grad_ptrs_dev, const long long* sizes_dev, const long long* chunk_prefix_dev,
+                        int count, long long total_chunks, float max_norm, float* out2_dev, void* workspace,
+                        size_t workspace_bytes, int do_clip, cadl_stream_t stream) {
+    if (!grad_ptrs_dev || !sizes_dev || !chunk_prefix_dev || !out2_dev || !workspace) return CADL_ERR_NULL;
+    if (count < 1 || total_chunks < 1) return CADL_ERR_SHAPE;
+    if (!aligned(workspace, 256) || workspace_bytes < cadl_clip_workspace_bytes()) return CADL_ERR_WORKSPACE;
+    ClipArgs a{};
+    a.ptrs = grad_ptrs_dev; a.sizes = sizes_dev; a.chunk_prefix = chunk_prefix_dev; a.count = count;
+    a.max_norm = max_norm; a.out = out2_dev;
+    a.hdr = reinterpret_cast<WsHeader*>(workspace);
+    a.part = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
+    int grid = 148 * 8;
+    if ((long long)grid > total_chunks) grid = (int)total_chunks;
+    a.part_rows = grid;
+    cudaStream_t st = (cudaStream_t)stream;
+    gradnorm_kernel<<<grid, 256, 0, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || !do_clip) return cuda_rc(e);
+    gradscale_kernel<<<grid, 256, 0, st>>>(a);
+    return cuda_rc(cudaGetLastError());
 }
 
 int cadl_photometric_fwd_bwd(const float* pred, const float* K, int k_batched, const float* T,

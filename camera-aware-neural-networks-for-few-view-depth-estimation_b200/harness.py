@@ -56,6 +56,9 @@ class StepHarness:
         L.cadh_time_steps.argtypes = [C.POINTER(_Cfg), vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
                                       C.c_char_p, C.c_int]
         L.cadh_set_num_threads.argtypes = [C.c_int]
+        if hasattr(L, "cadh_clip_grad_norm"):        # drop-in build only ("next" rows)
+            L.cadh_clip_grad_norm.argtypes = [C.c_int, C.c_int, vp, vp, C.c_float, C.c_int, vp, vp, C.c_char_p, C.c_int]
+            L.cadh_batch_prep.argtypes = [C.c_int] * 6 + [vp] * 6 + [C.c_char_p, C.c_int]
         self.L = L
 
     # ------------------------------------------------------------------
@@ -133,6 +136,34 @@ class StepHarness:
         if rc:
             self._raise(err)
         return [float(x) for x in out], [int(x) for x in cnt]
+
+    def clip_grad_norm(self, device: int, grads, max_norm: float, clip: bool = True):
+        """FusedGradClipper (host/training/grad_clip.h) over a list of gradient arrays -> (norm, coef, clipped)."""
+        gs = [_f32(g).reshape(-1) for g in grads]
+        outs = [np.empty_like(g) for g in gs]
+        n = len(gs)
+        inp = (C.c_void_p * n)(*[g.ctypes.data for g in gs])
+        outp = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        sizes = (C.c_int64 * n)(*[g.size for g in gs])
+        out2 = (C.c_float * 2)()
+        err = C.create_string_buffer(2048)
+        rc = self.L.cadh_clip_grad_norm(device, n, inp, sizes, max_norm, int(clip), out2, outp, err, len(err))
+        if rc:
+            self._raise(err)
+        return float(out2[0]), float(out2[1]), outs
+
+    def batch_prep(self, device: int, rgb, depth, K, H: int, W: int):
+        """resizeBatchOnDevice (host/data/batch_prep.h)."""
+        rgb, depth, K = _f32(rgb), _f32(depth), _f32(K)
+        B, _, h, w = rgb.shape
+        ro = np.empty((B, 3, H, W), np.float32)
+        do = np.empty((B, 1, H, W), np.float32)
+        ko = np.empty((B, 3, 3), np.float32)
+        err = C.create_string_buffer(2048)
+        rc = self.L.cadh_batch_prep(device, B, h, w, H, W, _p(rgb), _p(depth), _p(K), _p(ro), _p(do), _p(ko), err, len(err))
+        if rc:
+            self._raise(err)
+        return ro, do, ko
 
     def time_steps(self, cfg: StepCfg, pred, gt, rgb, K, mask=None, with_metrics=False, include_h2d=False,
                    warmup=1, iters=5):

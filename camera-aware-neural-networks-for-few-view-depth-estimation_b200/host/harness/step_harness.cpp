@@ -30,6 +30,8 @@
 #include "evaluation/depth_metrics.h"
 #ifdef CADL_DROPIN
 #include "training/validation_metrics.h"
+#include "training/grad_clip.h"
+#include "data/batch_prep.h"
 #endif
 
 using namespace camera_aware_depth;
@@ -362,5 +364,51 @@ int cadh_time_steps(const cadh_step_cfg* cfg, const float* pred, const float* gt
         return fail(err, errlen, e);
     }
 }
+
+#ifdef CADL_DROPIN
+// "next" rows through their C++ wrappers (host/training/grad_clip.h, host/data/batch_prep.h)
+int cadh_clip_grad_norm(int device, int count, const float* const* grads_host, const int64_t* sizes, float max_norm,
+                        int do_clip, float* out2, float* const* grads_out_host, char* err, int errlen) {
+    try {
+        auto dev = pick_device(device);
+        std::vector<torch::Tensor> params;
+        for (int i = 0; i < count; ++i) {
+            auto p = torch::zeros({sizes[i]}, torch::TensorOptions().device(dev)).set_requires_grad(true);
+            p.mutable_grad() = torch::from_blob(const_cast<float*>(grads_host[i]), {sizes[i]}, torch::kFloat32).to(dev).clone();
+            params.push_back(p);
+        }
+        FusedGradClipper clipper;
+        auto out = clipper.run(params, max_norm, do_clip != 0).to(torch::kCPU);
+        out2[0] = out[0].item<float>();
+        out2[1] = out[1].item<float>();
+        for (int i = 0; i < count; ++i) {
+            auto g = params[i].grad().to(torch::kCPU).contiguous();
+            std::memcpy(grads_out_host[i], g.data_ptr<float>(), sizeof(float) * g.numel());
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        return fail(err, errlen, e);
+    }
+}
+
+int cadh_batch_prep(int device, int B, int h, int w, int H, int W, const float* rgb, const float* depth, const float* K,
+                    float* rgb_out, float* depth_out, float* K_out, char* err, int errlen) {
+    try {
+        auto dev = pick_device(device);
+        auto r = host_view(rgb, {B, 3, h, w}).to(dev);
+        auto d = host_view(depth, {B, 1, h, w}).to(dev);
+        auto k = host_view(K, {B, 3, 3}).to(dev);
+        auto res = resizeBatchOnDevice(r, d, k, H, W);
+        auto ro = std::get<0>(res).to(torch::kCPU).contiguous(), dd = std::get<1>(res).to(torch::kCPU).contiguous(),
+             ko = std::get<2>(res).to(torch::kCPU).contiguous();
+        std::memcpy(rgb_out, ro.data_ptr<float>(), sizeof(float) * ro.numel());
+        std::memcpy(depth_out, dd.data_ptr<float>(), sizeof(float) * dd.numel());
+        std::memcpy(K_out, ko.data_ptr<float>(), sizeof(float) * ko.numel());
+        return 0;
+    } catch (const std::exception& e) {
+        return fail(err, errlen, e);
+    }
+}
+#endif
 
 }  // extern "C"

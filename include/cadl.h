@@ -173,6 +173,25 @@ int cadl_metrics(const float* pred, const float* gt, const uint8_t* mask, size_t
 int cadl_rays_from_K(const float* K, int k_batched, const float* pose, int B, int H, int W,
                      int layout, float* out, cadl_stream_t stream);
 
+/* ---- "next" rows of the scope table: the steps either side of the loss path ---- */
+
+/* SunRGBDLoader::resizeSample on the device (src/data/sunrgbd_loader.cpp:445-489): rgb (B,3,h,w) -> (B,3,H,W)
+ * bilinear align_corners=false, depth (B,1,h,w) -> (B,1,H,W) nearest, K (B,3,3) rescaled (fx,cx by W/w; fy,cy by
+ * H/h).  One launch after the H2D copy instead of per-sample host interpolate calls. */
+int cadl_batch_prep(const float* rgb_in, const float* depth_in, const float* K_in, int B, int h, int w, int H, int W,
+                    float* rgb_out, float* depth_out, float* K_out, cadl_stream_t stream);
+
+/* torch::nn::utils::clip_grad_norm_(params, max_norm) and the trainers' computeGradientNorm
+ * (src/training/tensorboard_trainer_enhanced.h:300-302, :560-571) over `count` gradient tensors without a host
+ * sync.  grad_ptrs_dev / sizes_dev: device arrays of pointers and element counts; chunk_prefix_dev: device
+ * array of count+1 exclusive prefix sums of ceil(size/4096) (total_chunks = its last entry).  out2_dev receives
+ * {total_norm, clip_coef}; with do_clip != 0 every gradient is multiplied by clip_coef = min(max_norm /
+ * (total_norm + 1e-6), 1).  Workspace: cadl_clip_workspace_bytes(), zeroed once. */
+size_t cadl_clip_workspace_bytes(void);
+int cadl_clip_grad_norm(float* const* grad_ptrs_dev, const long long* sizes_dev, const long long* chunk_prefix_dev,
+                        int count, long long total_chunks, float max_norm, float* out2_dev, void* workspace,
+                        size_t workspace_bytes, int do_clip, cadl_stream_t stream);
+
 /* Builder extension (NOT in the reference, whose forwardPhotometric is a stub returning zeros,
  * depth_loss.h:343-351): photometric reprojection  back-project -> [R|t] -> project -> bilinear
  * sample -> L1 residual, with explicit backward to depth.  T (B,4,4) row-major target->source.

@@ -290,3 +290,29 @@ def photometric_reprojection(pred, intrinsics, T, source_image, target_image, ep
     if sel.numel() == 0:
         return torch.zeros(1, dtype=dt, device=dev)
     return sel.mean()
+
+
+# --------------------------------------------------------------------------------------------
+# "next" rows.  The reference ops themselves: ATen interpolate / clip_grad_norm_.
+# --------------------------------------------------------------------------------------------
+def resize_sample(rgb, depth, K, H: int, W: int):
+    """SunRGBDLoader::resizeSample, batched         reference src/data/sunrgbd_loader.cpp:445-489"""
+    h, w = rgb.shape[-2:]
+    rgb2 = F.interpolate(rgb, size=(H, W), mode="bilinear", align_corners=False)     # :453-459
+    depth2 = F.interpolate(depth, size=(H, W), mode="nearest")                        # :461-467
+    sx = torch.tensor(float(W), dtype=torch.float32) / w                              # :480  (float division)
+    sy = torch.tensor(float(H), dtype=torch.float32) / h                              # :481
+    K2 = K.clone()                                                                    # :483
+    K2[:, 0, 0] = K[:, 0, 0] * sx                                                     # :484
+    K2[:, 1, 1] = K[:, 1, 1] * sy                                                     # :485
+    K2[:, 0, 2] = K[:, 0, 2] * sx                                                     # :486
+    K2[:, 1, 2] = K[:, 1, 2] * sy                                                     # :487
+    return rgb2, depth2, K2
+
+
+def clip_grad_norm(grads, max_norm: float):
+    """torch::nn::utils::clip_grad_norm_ (tensorboard_trainer_enhanced.h:300-302) and computeGradientNorm (:560-571).
+    Returns (total_norm, clipped grads)."""
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads)).float()
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    return total, [g * coef for g in grads]

@@ -105,3 +105,37 @@ def test_timing_loop_runs(pkg, host):
     ms, last = host.time_steps(pkg.StepCfg(device=0, term=0), z["pred"], z["gt"], z["rgb"], z["K"], with_metrics=True,
                                include_h2d=True, warmup=2, iters=3)
     assert len(ms) == 3 and all(m > 0 for m in ms) and np.isfinite(last)
+
+
+def test_fused_grad_clipper_cpp_wrapper(host):
+    """host/training/grad_clip.h against torch.nn.utils.clip_grad_norm_ semantics (oracle.clip_grad_norm)."""
+    import torch
+    from oracle import oracle_torch as O
+    rng = np.random.default_rng(5)
+    grads = [rng.standard_normal(n).astype(np.float32) * s for n, s in ((7, 1.0), (4096, 0.1), (100003, 0.01), (1, 3.0))]
+    for max_norm in (0.5, 1e6):
+        norm, coef, clipped = host.clip_grad_norm(0, grads, max_norm)
+        rn, rg = O.clip_grad_norm([torch.from_numpy(g) for g in grads], max_norm)
+        assert rel_err(norm, float(rn)) <= TOL
+        assert rel_err(coef, min(1.0, max_norm / (float(rn) + 1e-6))) <= TOL
+        for a, b in zip(clipped, rg):
+            np.testing.assert_allclose(a, b.numpy(), rtol=2e-6, atol=0)
+    norm, _, same = host.clip_grad_norm(0, grads, 0.5, clip=False)
+    for a, b in zip(same, grads):
+        assert np.array_equal(a, b)
+
+
+def test_batch_prep_cpp_wrapper(pkg, host):
+    """host/data/batch_prep.h against the resizeSample restatement (sunrgbd_loader.cpp:445-489)."""
+    import torch
+    from oracle import oracle_torch as O
+    rng = np.random.default_rng(9)
+    B, h, w, H, W = 2, 53, 71, 48, 64
+    rgb = rng.random((B, 3, h, w), dtype=np.float32)
+    dep = (rng.random((B, 1, h, w), dtype=np.float32) * 9 + 0.2).astype(np.float32)
+    K = np.tile(np.array([[60.0, 0, 35.5], [0, 61.0, 26.5], [0, 0, 1]], np.float32), (B, 1, 1))
+    ro, do, ko = host.batch_prep(0, rgb, dep, K, H, W)
+    r, d, k = O.resize_sample(torch.from_numpy(rgb), torch.from_numpy(dep), torch.from_numpy(K), H, W)
+    np.testing.assert_allclose(ro, r.numpy(), rtol=0, atol=2e-6)
+    assert np.array_equal(do, d.numpy())
+    np.testing.assert_allclose(ko, k.numpy(), rtol=1e-6)

@@ -109,3 +109,50 @@ def test_photometric_stub_is_kept(pkg, host_stub=None):
     src = open(os.path.join(ROOT, pkg.__name__.split(".")[0], "host", "loss", "depth_loss.h")).read()
     body = re.search(r"forwardPhotometric\(.*?\{(.*?)\n    \}", src, flags=re.S).group(1)
     assert "torch::zeros(1" in body
+
+
+# ---------------------------------------------------------------------------------------------------------
+# "next" rows: on-device batch prep, fused grad-norm clip
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("src,dst", [((530, 730), (480, 640)), ((427, 561), (240, 320)), ((240, 320), (480, 640))])
+def test_batch_prep_matches_aten_interpolate(pkg, oracle, src, dst):
+    (h, w), (H, W) = src, dst
+    g = torch.Generator().manual_seed(3)
+    rgb = torch.rand(3, 3, h, w, generator=g)
+    depth = torch.rand(3, 1, h, w, generator=g) * 9 + 0.3
+    depth[torch.rand(3, 1, h, w, generator=g) < 0.15] = 0.0
+    K = pkg.synth.make_batch(3, h, w, seed=2)["K"]
+    d = torch.device("cuda:0")
+    r2, d2, K2 = pkg.batch_prep(rgb.to(d), depth.to(d), K.to(d), H, W)
+    for dev in ("cpu", "cuda"):
+        ro, do, Ko = oracle.resize_sample(rgb.to(dev), depth.to(dev), K.to(dev), H, W)
+        assert torch.equal(d2.cpu(), do.cpu())                       # nearest: identical source indices
+        assert float((r2.cpu() - ro.cpu()).abs().max()) <= 2e-6      # bilinear weights to rounding
+        assert torch.equal(K2.cpu(), Ko.cpu())
+
+
+def test_clip_grad_norm_matches_torch(pkg, oracle):
+    d = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(11)
+    shapes = [(64, 3, 3, 3), (64,), (128, 64, 3, 3), (1,), (4097,), (512, 512, 3, 3), (7, 5)]
+    for scale, max_norm in ((1.0, 1.0), (1e-4, 1.0), (3.0, 0.5)):
+        grads = [(torch.randn(*s, generator=g) * scale).to(d) for s in shapes]
+        # the reference op itself on parameters carrying these gradients
+        params = [torch.nn.Parameter(torch.zeros_like(x)) for x in grads]
+        for prm, x in zip(params, grads):
+            prm.grad = x.clone()
+        total_ref = torch.nn.utils.clip_grad_norm_(params, max_norm)
+        tot_o, clipped_o = oracle.clip_grad_norm([x.clone() for x in grads], max_norm)
+        clipper = pkg.GradClipper(grads)
+        out = clipper(max_norm).cpu()
+        assert rel_err(float(out[0]), float(tot_o)) <= 1e-6 and rel_err(float(out[0]), float(total_ref)) <= 1e-5
+        coef = min(max_norm / (float(tot_o) + 1e-6), 1.0)
+        assert rel_err(float(out[1]), coef) <= 1e-6
+        for a, b, prm in zip(grads, clipped_o, params):
+            assert float((a - b).abs().max()) <= 1e-6 * max(float(b.abs().max()), 1e-30)
+            assert float((a - prm.grad).abs().max()) <= 1e-5 * max(float(prm.grad.abs().max()), 1e-30)
+    # norm only (computeGradientNorm): gradients untouched
+    grads = [torch.randn(1000, generator=g).to(d)]
+    keep = grads[0].clone()
+    out = pkg.GradClipper(grads)(0.1, clip=False).cpu()
+    assert torch.equal(grads[0], keep) and rel_err(float(out[0]), float(keep.double().norm())) <= 1e-6

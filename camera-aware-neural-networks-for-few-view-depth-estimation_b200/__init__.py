@@ -247,7 +247,8 @@ def metrics(pred, gt, mask=None, which: int = METRICS_EVAL | METRICS_TRAIN, min_
 
 def force_generic(on):
     """Test hook (bit mask): 1 = route phase B through the generic kernel even for aligned shapes;
-    2 = keep the fast kernel but stage tiles with cp.async instead of TMA; 4 = warp-specialised persistent kernel."""
+    8 = the one-CTA-per-tile fast kernel instead of the streaming split (default for aligned shapes); with 8:
+    2 = stage tiles with cp.async instead of TMA, 4 = warp-specialised persistent tile kernel."""
     lib().cadl_debug_force_generic(int(on))
 
 

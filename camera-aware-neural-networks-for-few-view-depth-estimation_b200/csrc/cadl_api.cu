@@ -10,6 +10,7 @@
 #include "cadl_phase_b.cuh"
 #include "cadl_phase_b_fast.cuh"
 #include "cadl_phase_b_ws.cuh"
+#include "cadl_phase_b_stream.cuh"
 #include "cadl_rays.cuh"
 #include "cadl_photometric.cuh"
 #include "cadl_next.cuh"
@@ -68,10 +69,21 @@ struct Ws {
     double* b_part() const { return reinterpret_cast<double*>(base + L.b_part); }
     double* img_sm() const { return reinterpret_cast<double*>(base + L.img_sm); }
     float* img_off() const { return reinterpret_cast<float*>(base + L.img_off); }
+    bool has_pyr() const { return L.pyr_blocks > 0; }
+    PyrArrays pyr() const {
+        PyrArrays p;
+        for (int s = 0; s < 3; ++s) {
+            p.lp[s] = reinterpret_cast<float*>(base + L.pyr_lp[s]);
+            p.lg[s] = reinterpret_cast<float*>(base + L.pyr_lg[s]);
+            p.rq[s] = reinterpret_cast<float*>(base + L.pyr_rq[s]);
+        }
+        p.c1 = reinterpret_cast<float*>(base + L.pyr_c1);
+        return p;
+    }
 };
 
-constexpr int kPointBlocks = 148 * 8;
 int g_force_generic = 0;
+int g_force_tile = 0;       // bit 3: the one-CTA-per-tile fast kernel instead of the streaming split
 int g_force_no_tma = 0;
 int g_use_ws = 0;           // bit 2: warp-specialised persistent kernel instead of the plain one-tile-per-CTA fast kernel     // bit 1 of cadl_debug_force_generic: keep the fast kernel but stage with cp.async   // cadl_debug_force_generic(): tests compare the two phase-B kernels
 
@@ -214,6 +226,29 @@ cudaError_t launch_fast(PhaseBArgs& a, cudaStream_t st) {
     return a.mask ? launch_fast_m<F, true>(a, st) : launch_fast_m<F, false>(a, st);
 }
 
+// streaming split of the fast path: pooled pyramid -> coarse coefficients -> full-resolution pass (cadl_phase_b_stream.cuh)
+template <int F>
+cudaError_t launch_stream(PhaseBArgs& a, const Ws& ws, cudaStream_t st) {
+    const PyrArrays py = ws.pyr();
+    const int nblk = ws.L.pyr_blocks, wpi = ws.L.wpi;
+    pyr_pool_kernel<<<nblk, 256, 0, st>>>(a.pred, a.gt, a.B, a.H, a.W, a.eps_grad, py);
+    PyrCoefArgs ca{};
+    ca.py = py; ca.B = a.B; ca.H = a.H; ca.W = a.W;
+    for (int s = 0; s < 4; ++s) { ca.inv_nx[s] = a.inv_nx[s]; ca.inv_ny[s] = a.inv_ny[s]; }
+    ca.wg = 0.25f * a.w_grad * a.upstream;          // 1/num_scales * weight * upstream
+    ca.b_part = a.b_part; ca.row0 = a.B * wpi;
+    pyr_coef_kernel<<<nblk, 256, 0, st>>>(ca);
+    StreamArgs sa{};
+    sa.c1 = py.c1; sa.wpi = wpi; sa.nstrip = (a.W + 127) / 128;
+    a.tiles_x = wpi; a.tiles_y = 1;                  // finalize_results: partial rows per image
+    a.b_rows = a.B * wpi + nblk;
+    sa.rows_total = a.b_rows;
+    const int grid = (a.B * wpi + kThreadsB / 32 - 1) / (kThreadsB / 32);
+    if (a.mask) phase_b_stream_kernel<F, true><<<grid, kThreadsB, 0, st>>>(a, sa);
+    else phase_b_stream_kernel<F, false><<<grid, kThreadsB, 0, st>>>(a, sa);
+    return cudaGetLastError();
+}
+
 template <int F>
 cudaError_t launch_point_fast(PhaseBArgs& a, cudaStream_t st) {
     // (blocks per image, B) with ~8 CTAs per SM in total; a_rows = grid size (partial rows, ticket)
@@ -333,10 +368,11 @@ int run_grad(const float* pred, const float* gt, const float* rgb, const float* 
     if (fast) {
         a.tiles_x = (W + FTW - 1) / FTW; a.tiles_y = (H + FTH - 1) / FTH;
         a.b_rows = a.tiles_x * a.tiles_y * B;
+        const bool stream = (t & CADL_TERM_GRAD) && ws.has_pyr() && !g_force_tile;
         switch (t) {
-            case CADL_TERM_ALL: e = launch_fast<15>(a, st); break;
-            case CADL_TERM_SI | CADL_TERM_GRAD | CADL_TERM_SMOOTH: e = launch_fast<7>(a, st); break;
-            case CADL_TERM_GRAD: e = launch_fast<FB_GRAD>(a, st); break;
+            case CADL_TERM_ALL: e = stream ? launch_stream<15>(a, ws, st) : launch_fast<15>(a, st); break;
+            case CADL_TERM_SI | CADL_TERM_GRAD | CADL_TERM_SMOOTH: e = stream ? launch_stream<7>(a, ws, st) : launch_fast<7>(a, st); break;
+            case CADL_TERM_GRAD: e = stream ? launch_stream<FB_GRAD>(a, ws, st) : launch_fast<FB_GRAD>(a, st); break;
             case CADL_TERM_SMOOTH: e = launch_fast<FB_SMOOTH>(a, st); break;
             default: return CADL_ERR_UNSUPPORTED;
         }
@@ -386,6 +422,7 @@ int cadl_version(void) { return CADL_VERSION; }
 void cadl_debug_force_generic(int on) {
     g_force_generic = on & 1;
     g_force_no_tma = (on >> 1) & 1;
+    g_force_tile = (on >> 3) & 1;
     g_use_ws = (on >> 2) & 1;
 }
 size_t cadl_sizeof_params(void) { return sizeof(cadl_params); }
@@ -412,22 +449,12 @@ const char* cadl_error_string(int code) {
 size_t cadl_workspace_bytes(int B, int H, int W) {
     if (B < 1 || H < 1 || W < 1) return 0;
     WsLayout L = layout_for(B, H, W);
-    // the pointwise kernel writes kPointBlocks partial rows
-    size_t need_b = sizeof(double) * (size_t)kPointBlocks * BF_COUNT;
-    size_t have_b = L.img_sm - L.b_part;
-    size_t extra = need_b > have_b ? align_up(need_b - have_b, 256) : 0;
-    return L.total + extra + 256;
+    return L.total + 256;
 }
 
 static Ws make_ws(void* workspace, int B, int H, int W) {
     Ws ws;
     ws.L = layout_for(B, H, W);
-    size_t need_b = sizeof(double) * (size_t)kPointBlocks * BF_COUNT;
-    size_t have_b = ws.L.img_sm - ws.L.b_part;
-    if (need_b > have_b) {
-        size_t extra = align_up(need_b - have_b, 256);
-        ws.L.img_sm += extra; ws.L.img_off += extra; ws.L.total += extra;
-    }
     ws.base = static_cast<char*>(workspace);
     return ws;
 }

@@ -94,8 +94,10 @@ size_t cadl_sizeof_params(void);
 size_t cadl_sizeof_results(void);
 const char* cadl_error_string(int code);
 /* Test hook (bit mask): 1 = always take the generic phase-B kernel (any shape/alignment) instead of the
- * aligned fast path; 2 = fast path stages tiles with cp.async instead of TMA; 4 = warp-specialised persistent
- * kernel (cadl_phase_b_ws.cuh) instead of the plain one-tile-per-CTA fast kernel.  All variants must produce the same values.  Process-global; not for production use. */
+ * aligned fast path; 8 = fast path as ONE tile kernel (cadl_phase_b_fast.cuh) instead of the streaming split
+ * (cadl_phase_b_stream.cuh); together with 8: 2 = stage tiles with cp.async instead of TMA, 4 = warp-specialised
+ * persistent tile kernel (cadl_phase_b_ws.cuh).  All variants must produce the same values.  Process-global;
+ * not for production use. */
 void cadl_debug_force_generic(int on);
 /* Test hook: counts (into *mismatches_dev, a device uint64 the caller zeroed) the inputs with bit pattern in
  * [lo_bits, hi_bits] for which a device-math replica differs from the CUDA library form.

@@ -41,7 +41,7 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    hbm = float(peaks.get("hbm_gbps_burst", peaks.get("hbm_gbps", 6452.5)))
+    hbm = float(peaks.get("hbm_gbs", 6452.5))
     flush = torch.zeros(256 << 20, dtype=torch.uint8, device=dev).view(torch.float32)
 
     B, h, w, H, W = 32, 530, 730, 480, 640

@@ -11,7 +11,7 @@ dev = torch.device("cuda:0")
 for (B, H, W) in [(2, 48, 128), (2, 56, 72), (1, 37, 53), (2, 8, 8), (3, 96, 160)]:
     b = pkg.synth.make_batch(B, H, W, seed=B * H, device=dev)
     mask = (torch.rand(B, 1, H, W, device=dev) < 0.7)
-    for mode in (0, 1, 2, 4):
+    for mode in (0, 1, 8, 10, 12):
         pkg.force_generic(mode)
         for terms, K in ((pkg.TERM_ALL, b["K"]), (pkg.TERM_SI | pkg.TERM_GRAD | pkg.TERM_SMOOTH, None),
                          (pkg.TERM_GRAD, None), (pkg.TERM_SMOOTH, None), (pkg.TERM_SI, None), (pkg.TERM_REPROJ, b["K"]),

@@ -251,6 +251,14 @@ struct StreamArgs {
     int rows_total;      // partial rows finalize_results sums (B * wpi + rows of pyr_coef_kernel)
 };
 
+// One image row as a lane holds it: its own 4 pixels, the right neighbour, and the end lanes' halo pixel.
+struct StreamRow {
+    float p[5], g[4], I[3][5];     // pred (+ right neighbour), gt, rgb (+ right neighbour)
+    float lp[4], lg[4];            // log(clamp(pred)), log(clamp(gt))          depth_loss.h:115-116
+    float hp, hg, hI[3];           // halo pixel: lane 0 its left neighbour, the last lane its right neighbour
+    float hlp, hlg;                // logs of the halo pixel
+};
+
 template <int F, bool HAS_MASK>
 __global__ void __launch_bounds__(kThreadsB, 2) phase_b_stream_kernel(const PhaseBArgs a, const StreamArgs sa) {
     __shared__ double s_d[8];
@@ -274,7 +282,8 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_stream_kernel(const Phas
         const float* __restrict__ gtb = a.gt + img;
         const float* __restrict__ rgbb = SMOOTH ? a.rgb + (size_t)b * 3 * H * W : nullptr;
         const float* __restrict__ c1b = sa.c1 + (size_t)b * (H >> 1) * (W >> 1);
-        const int plane = H * W, W1 = W >> 1;
+        float* __restrict__ gradb = a.grad ? a.grad + img : nullptr;
+        const int plane = H * W, W1 = W >> 1;                    // 3*H*W < 2^31 (checked on the host)
         const float up = a.upstream;
 
         // scalars derived from the phase-A statistics, weights and upstream folded in
@@ -314,13 +323,16 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_stream_kernel(const Phas
             const int ye = (end - cur < H - ys) ? ys + (end - cur) : H;     // rows [ys, ye) of this strip
             cur += ye - ys;
 
+            // Lanes right of the image (partial last strip) load the last in-image float4 instead: they neither
+            // store nor count, and the last in-image lane takes its right neighbour from its halo pixel.
             const int gx0 = strip * 128 + 4 * lane;
             const bool lane_in = gx0 < W;                       // W % 4 == 0: a lane is fully inside or outside
-            const int gxr = clampi(gx0 + 4, 0, W - 1);                  // right neighbour column of the last lane
-            const bool right_in = gx0 + 4 < W;
-            const bool endlane = (lane == 31) || (lane == 0 && gx0 >= 1);
-            const int hx = (lane == 31) ? gxr : (gx0 >= 1 ? gx0 - 1 : 0);     // column of the end lanes' halo pixel
-            const bool h_rgb_ok = (lane == 31) ? right_in : true;
+            const int gxc = lane_in ? gx0 : W - 4;
+            const bool lastlane = (lane == 31) || (gx0 + 4 >= W);
+            // halo pixel: right neighbour for the last lane (clamped to the image: the pixel itself at the right
+            // border, so that edge vanishes), left neighbour for lane 0 (itself at the left border)
+            const int hx = lastlane ? (gx0 + 4 < W ? gx0 + 4 : W - 1) : (gx0 >= 1 ? gx0 - 1 : 0);
+            const bool left_edge = (lane == 0) && (gx0 >= 1);    // lane 0 evaluates the edge to its left neighbour strip
             float axk[4] = {0.f, 0.f, 0.f, 0.f}, xhk[4] = {0.f, 0.f, 0.f, 0.f};
             if constexpr (RP) {
 #pragma unroll
@@ -330,132 +342,84 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_stream_kernel(const Phas
                 }
             }
 
-            // ---- row state ----
-            float pc[5], gc[4], Ic[3][5];       // current row: own 4 (+ right neighbour)
-            float pn[5], gn[4], In[3][5];       // next row
-            float hn_p = 0.f, hn_g = 0.f, hn_I[3] = {0.f, 0.f, 0.f};   // end lanes' halo pixel of the next row
-            float hc_p = 0.f, hc_I[3] = {0.f, 0.f, 0.f};               // ... of the current row
-            float hl_p = 0.f, hl_g = 0.f;                              // logs of the current row's halo pixel
-            float lpc[4], lgc[4];                                      // logs of the current row
-            float sy_up[4] = {0.f, 0.f, 0.f, 0.f}, ty_up[4] = {0.f, 0.f, 0.f, 0.f};
-
-            // issue the global loads of one image row (clamped at the borders); no use of the values here
-            auto fetch = [&](int gy_raw, float (&p)[5], float (&g)[4], float (&I)[3][5], float& hp, float& hg, float (&hI)[3]) {
-                const bool in_img = (gy_raw >= 0) && (gy_raw < H);
-                const int ro = clampi(gy_raw, 0, H - 1) * W;
-                if (lane_in) {
-                    const float4 p4 = __ldg(reinterpret_cast<const float4*>(predb + ro + gx0));
-                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gtb + ro + gx0));
-                    p[0] = p4.x; p[1] = p4.y; p[2] = p4.z; p[3] = p4.w;
-                    g[0] = g4.x; g[1] = g4.y; g[2] = g4.z; g[3] = g4.w;
-                } else {   // lanes right of the image hold the replicated border pixel (their edges vanish)
-                    const float ps = __ldg(predb + ro + W - 1), gs = __ldg(gtb + ro + W - 1);
-                    p[0] = p[1] = p[2] = p[3] = ps;
-                    g[0] = g[1] = g[2] = g[3] = gs;
-                }
+            // issue the global loads of one image row; rows outside the image are the border row again (every
+            // vertical edge across the border then has residual exactly 0).  No use of the values here.
+            auto fetch = [&](int off, int offh, StreamRow& R) {
+                const float4 p4 = __ldg(reinterpret_cast<const float4*>(predb + off));
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(gtb + off));
+                R.p[0] = p4.x; R.p[1] = p4.y; R.p[2] = p4.z; R.p[3] = p4.w;
+                R.g[0] = g4.x; R.g[1] = g4.y; R.g[2] = g4.z; R.g[3] = g4.w;
+                R.hp = __ldg(predb + offh);
+                R.hg = __ldg(gtb + offh);
                 if constexpr (SMOOTH) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (in_img && lane_in) v = ldg_stream(reinterpret_cast<const float4*>(rgbb + c * plane + ro + gx0));
-                        I[c][0] = v.x; I[c][1] = v.y; I[c][2] = v.z; I[c][3] = v.w;
-                    }
-                }
-                // the two lanes at the warp's ends also fetch the pixel beyond their end: lane 31 its right
-                // neighbour, lane 0 its left neighbour (same registers, same instructions, different lanes)
-                if (endlane) {
-                    hp = __ldg(predb + ro + hx);
-                    hg = __ldg(gtb + ro + hx);
-                    if constexpr (SMOOTH) {
-                        const bool ok = in_img && h_rgb_ok;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) hI[c] = ok ? __ldg(rgbb + c * plane + ro + hx) : 0.f;
+                        const float4 v = ldg_stream(reinterpret_cast<const float4*>(rgbb + c * plane + off));
+                        R.I[c][0] = v.x; R.I[c][1] = v.y; R.I[c][2] = v.z; R.I[c][3] = v.w;
+                        R.hI[c] = __ldg(rgbb + c * plane + offh);
                     }
                 }
             };
-            // logs of a row (depth_loss.h:115-116) and its right neighbours across lanes
-            auto finish_row = [&](float (&p)[5], const float (&g)[4], float (&I)[3][5], float hp, float hg, const float (&hI)[3],
-                                  float (&lp)[4], float (&lg)[4], float& hlp, float& hlg) {
-                const float2 a0 = log_exact2(make_float2(clamp_nan(p[0], eps_g, 1000.0f), clamp_nan(p[1], eps_g, 1000.0f)));
-                const float2 a1 = log_exact2(make_float2(clamp_nan(p[2], eps_g, 1000.0f), clamp_nan(p[3], eps_g, 1000.0f)));
-                const float2 b0 = log_exact2(make_float2(clamp_nan(g[0], eps_g, 1000.0f), clamp_nan(g[1], eps_g, 1000.0f)));
-                const float2 b1 = log_exact2(make_float2(clamp_nan(g[2], eps_g, 1000.0f), clamp_nan(g[3], eps_g, 1000.0f)));
-                const float2 hh = log_exact2(make_float2(clamp_nan(hp, eps_g, 1000.0f), clamp_nan(hg, eps_g, 1000.0f)));
-                lp[0] = a0.x; lp[1] = a0.y; lp[2] = a1.x; lp[3] = a1.y;
-                lg[0] = b0.x; lg[1] = b0.y; lg[2] = b1.x; lg[3] = b1.y;
-                hlp = hh.x; hlg = hh.y;
+            // logs of a row and its right neighbours across lanes -- called when the row's loads have landed
+            auto finish_row = [&](StreamRow& R) {
+                float2 v[5];
+                v[0] = make_float2(clamp_nan(R.p[0], eps_g, 1000.0f), clamp_nan(R.p[1], eps_g, 1000.0f));
+                v[1] = make_float2(clamp_nan(R.p[2], eps_g, 1000.0f), clamp_nan(R.p[3], eps_g, 1000.0f));
+                v[2] = make_float2(clamp_nan(R.g[0], eps_g, 1000.0f), clamp_nan(R.g[1], eps_g, 1000.0f));
+                v[3] = make_float2(clamp_nan(R.g[2], eps_g, 1000.0f), clamp_nan(R.g[3], eps_g, 1000.0f));
+                v[4] = make_float2(clamp_nan(R.hp, eps_g, 1000.0f), clamp_nan(R.hg, eps_g, 1000.0f));
+                log_exact2_n<5>(v);
+                R.lp[0] = v[0].x; R.lp[1] = v[0].y; R.lp[2] = v[1].x; R.lp[3] = v[1].y;
+                R.lg[0] = v[2].x; R.lg[1] = v[2].y; R.lg[2] = v[3].x; R.lg[3] = v[3].y;
+                R.hlp = v[4].x; R.hlg = v[4].y;
                 if constexpr (SMOOTH) {
-                    const float pr = __shfl_down_sync(0xffffffffu, p[0], 1);
-                    p[4] = (lane == 31) ? hp : pr;
+                    const float pr = __shfl_down_sync(0xffffffffu, R.p[0], 1);
+                    R.p[4] = lastlane ? R.hp : pr;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        const float ir = __shfl_down_sync(0xffffffffu, I[c][0], 1);
-                        I[c][4] = (lane == 31) ? hI[c] : ir;
+                        const float ir = __shfl_down_sync(0xffffffffu, R.I[c][0], 1);
+                        R.I[c][4] = lastlane ? R.hI[c] : ir;
                     }
                 }
             };
-            // terms of the vertical edges (current row -> next row)
-            auto yterms = [&](bool count, float (&sy)[4], float (&ty)[4], const float (&lpn)[4], const float (&lgn)[4]) {
+            // terms of the vertical edges (row C -> row N)
+            auto yterms = [&](bool count, const StreamRow& C, const StreamRow& N, float (&sy)[4], float (&ty)[4]) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const float e = (lpn[k] - lpc[k]) - (lgn[k] - lgc[k]);      // depth_loss.h:151-163
+                    const float e = (N.lp[k] - C.lp[k]) - (N.lg[k] - C.lg[k]);      // depth_loss.h:151-163
                     sy[k] = sgn3(e);
                     if (count) acc[BF_GY0] += fabsf(e);
                 }
                 if constexpr (SMOOTH) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const float s = fabsf(In[0][k] - Ic[0][k]) + fabsf(In[1][k] - Ic[1][k]) + fabsf(In[2][k] - Ic[2][k]);
+                        const float s = fabsf(N.I[0][k] - C.I[0][k]) + fabsf(N.I[1][k] - C.I[1][k]) + fabsf(N.I[2][k] - C.I[2][k]);
                         const float wy = ex2_approx(s * kExpScale);                 // depth_loss.h:218-227
-                        const float d = pn[k] - pc[k];
+                        const float d = N.p[k] - C.p[k];
                         ty[k] = wy * sgn3(d);
                         if (count) acc[BF_SMY] = fmaf(wy, fabsf(d), acc[BF_SMY]);
                     }
                 }
             };
 
-            // prologue: the row above this segment only contributes its lower edges
-            float lpn[4], lgn[4], hln_p, hln_g;
-            {
-                float hp0 = 0.f, hg0 = 0.f, hI0[3] = {0.f, 0.f, 0.f}, t0, t1;
-                fetch(ys - 1, pc, gc, Ic, hp0, hg0, hI0);
-                fetch(ys, pn, gn, In, hn_p, hn_g, hn_I);
-                finish_row(pc, gc, Ic, hp0, hg0, hI0, lpc, lgc, t0, t1);
-                finish_row(pn, gn, In, hn_p, hn_g, hn_I, lpn, lgn, hln_p, hln_g);
-                yterms(false, sy_up, ty_up, lpn, lgn);
-            }
-            auto roll = [&]() {
-                hc_p = hn_p; hl_p = hln_p; hl_g = hln_g;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) hc_I[c] = hn_I[c];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { lpc[k] = lpn[k]; lgc[k] = lgn[k]; gc[k] = gn[k]; }
-#pragma unroll
-                for (int k = 0; k < 5; ++k) pc[k] = pn[k];
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) Ic[c][k] = In[c][k];
-            };
-            roll();
-
-            for (int gy = ys; gy < ye; ++gy) {
+            // One row: C is the current row (complete), N receives the next one.  up: signed terms of the edges
+            // to the row above (from the previous step); dn: those to the row below (for the next step).
+            auto step = [&](int gy, StreamRow& C, StreamRow& N, const float (&sy_up)[4], const float (&ty_up)[4],
+                            float (&sy_dn)[4], float (&ty_dn)[4]) {
                 // 1. issue next row's loads; they are consumed at step 4, after ~2/3 of this row's arithmetic
-                fetch(gy + 1, pn, gn, In, hn_p, hn_g, hn_I);
+                const int rn = (gy + 1 < H ? gy + 1 : gy) * W;
+                fetch(rn + gxc, rn + hx, N);
                 uchar4 mk4 = make_uchar4(0, 0, 0, 0);
-                if constexpr (HAS_MASK) {
-                    if (lane_in) mk4 = __ldg(reinterpret_cast<const uchar4*>(a.mask + img + gy * W + gx0));
-                }
-                float2 ccv = make_float2(0.f, 0.f);
-                if (lane_in) ccv = __ldg(reinterpret_cast<const float2*>(c1b + (gy >> 1) * W1 + (gx0 >> 1)));
+                if constexpr (HAS_MASK) mk4 = __ldg(reinterpret_cast<const uchar4*>(a.mask + img + gy * W + gxc));
+                const float2 ccv = __ldg(reinterpret_cast<const float2*>(c1b + (gy >> 1) * W1 + (gxc >> 1)));
 
                 // 2. horizontal edges of the current row: each lane evaluates the four edges to the right of its
                 //    pixels; the sign of the edge to its left comes from the left lane
                 float gm[4], smg[4] = {0.f, 0.f, 0.f, 0.f};
                 {
-                    const float lr_p = __shfl_down_sync(0xffffffffu, lpc[0], 1), lr_g = __shfl_down_sync(0xffffffffu, lgc[0], 1);
-                    const float lpx[5] = {lpc[0], lpc[1], lpc[2], lpc[3], (lane == 31) ? hl_p : lr_p};
-                    const float lgx[5] = {lgc[0], lgc[1], lgc[2], lgc[3], (lane == 31) ? hl_g : lr_g};
+                    const float lr_p = __shfl_down_sync(0xffffffffu, C.lp[0], 1), lr_g = __shfl_down_sync(0xffffffffu, C.lg[0], 1);
+                    const float lpx[5] = {C.lp[0], C.lp[1], C.lp[2], C.lp[3], lastlane ? C.hlp : lr_p};
+                    const float lgx[5] = {C.lg[0], C.lg[1], C.lg[2], C.lg[3], lastlane ? C.hlg : lr_g};
                     float sx[5];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -464,10 +428,7 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_stream_kernel(const Phas
                         if (lane_in) acc[BF_GX0] += fabsf(e);
                     }
                     float sl = __shfl_up_sync(0xffffffffu, sx[4], 1);
-                    if (lane == 0) {
-                        sl = 0.f;                                 // left neighbour lives in another strip: evaluate that edge here
-                        if (gx0 >= 1) sl = sgn3((lpc[0] - hl_p) - (lgc[0] - hl_g));
-                    }
+                    if (lane == 0) sl = left_edge ? sgn3((C.lp[0] - C.hlp) - (C.lg[0] - C.hlg)) : 0.f;
                     sx[0] = sl;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) gm[k] = (sx[k] - sx[k + 1]) * inx0;
@@ -476,18 +437,18 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_stream_kernel(const Phas
                     float tx[5];                                  // tx[j]: edge (x_{j-1} -> x_j); j = 0 belongs to the left lane
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const float s = fabsf(Ic[0][k + 1] - Ic[0][k]) + fabsf(Ic[1][k + 1] - Ic[1][k]) + fabsf(Ic[2][k + 1] - Ic[2][k]);
+                        const float s = fabsf(C.I[0][k + 1] - C.I[0][k]) + fabsf(C.I[1][k + 1] - C.I[1][k]) + fabsf(C.I[2][k + 1] - C.I[2][k]);
                         const float wx = ex2_approx(s * kExpScale);                 // depth_loss.h:211-226
-                        const float d = pc[k + 1] - pc[k];
+                        const float d = C.p[k + 1] - C.p[k];
                         tx[k + 1] = wx * sgn3(d);
                         if (lane_in) acc[BF_SMX] = fmaf(wx, fabsf(d), acc[BF_SMX]);
                     }
                     float tl = __shfl_up_sync(0xffffffffu, tx[4], 1);
                     if (lane == 0) {
                         tl = 0.f;
-                        if (gx0 >= 1) {
-                            const float s = fabsf(Ic[0][0] - hc_I[0]) + fabsf(Ic[1][0] - hc_I[1]) + fabsf(Ic[2][0] - hc_I[2]);
-                            tl = ex2_approx(s * kExpScale) * sgn3(pc[0] - hc_p);
+                        if (left_edge) {
+                            const float s = fabsf(C.I[0][0] - C.hI[0]) + fabsf(C.I[1][0] - C.hI[1]) + fabsf(C.I[2][0] - C.hI[2]);
+                            tl = ex2_approx(s * kExpScale) * sgn3(C.p[0] - C.hp);
                         }
                     }
                     tx[0] = tl;
@@ -505,17 +466,17 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_stream_kernel(const Phas
                 float rpk[4], pw[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const float p = pc[k];
+                    const float p = C.p[k];
                     rpk[k] = rcp_approx(p);
                     float gsum = (k < 2 ? ccv.x : ccv.y);
                     if constexpr (SI) {
-                        const float g = gc[k];
+                        const float g = C.g[k];
                         const bool m = HAS_MASK ? um[k] : (g > eps_g);        // eps_si == eps_grad on this path
-                        const float d = lpc[k] - lgc[k];
+                        const float d = C.lp[k] - C.lg[k];
                         if (m && in_range_pos(p, eps_g, 1000.0f)) gsum = fmaf(fmaf(c1, d, c2), rpk[k], gsum);
                     }
                     if constexpr (RP) {
-                        const float g = gc[k];
+                        const float g = C.g[k];
                         const bool m = HAS_MASK ? um[k] : (g > eps_r);
                         if (m && lane_in) {
                             // same operations, same order as depth_loss.h:299-315 (see cadl_phase_b.cuh)
@@ -542,25 +503,39 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_stream_kernel(const Phas
                 }
 
                 // 4. the next row has landed: its logs, the vertical edges, assembly and the 128-bit store
-                finish_row(pn, gn, In, hn_p, hn_g, hn_I, lpn, lgn, hln_p, hln_g);
-                float sy_dn[4], ty_dn[4] = {0.f, 0.f, 0.f, 0.f};
-                yterms(lane_in, sy_dn, ty_dn, lpn, lgn);
+                finish_row(N);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ty_dn[k] = 0.f;
+                yterms(lane_in, C, N, sy_dn, ty_dn);
                 float out[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     float gsum = pw[k];
                     if constexpr (SMOOTH) gsum += fmaf(ty_up[k] - ty_dn[k], sny, smg[k]);
                     const float gmk = fmaf(sy_up[k] - sy_dn[k], iny0, gm[k]);
-                    gsum = in_range_pos(pc[k], eps_g, 1000.0f) ? fmaf(gmk, rpk[k], gsum) : gsum;   // clamp backward
+                    gsum = in_range_pos(C.p[k], eps_g, 1000.0f) ? fmaf(gmk, rpk[k], gsum) : gsum;   // clamp backward
                     out[k] = gsum;
                 }
-                if (a.grad && lane_in)
-                    *reinterpret_cast<float4*>(a.grad + img + gy * W + gx0) = make_float4(out[0], out[1], out[2], out[3]);
+                if (gradb && lane_in)
+                    *reinterpret_cast<float4*>(gradb + gy * W + gx0) = make_float4(out[0], out[1], out[2], out[3]);
+            };
 
-                // roll the row state
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { sy_up[k] = sy_dn[k]; ty_up[k] = ty_dn[k]; }
-                roll();
+            // prologue: the row above this segment only contributes its lower edges
+            StreamRow RA, RB;
+            float u0s[4], u0t[4] = {0.f, 0.f, 0.f, 0.f}, u1s[4], u1t[4];
+            {
+                const int r0 = (ys > 0 ? ys - 1 : 0) * W, r1 = ys * W;
+                fetch(r0 + gxc, r0 + hx, RB);
+                fetch(r1 + gxc, r1 + hx, RA);
+                finish_row(RB);
+                finish_row(RA);
+                yterms(false, RB, RA, u0s, u0t);
+            }
+            // two rows per trip, the two row buffers and the two edge buffers trading places: no register copies
+            for (int gy = ys; gy < ye; gy += 2) {
+                step(gy, RA, RB, u0s, u0t, u1s, u1t);
+                if (gy + 1 >= ye) break;
+                step(gy + 1, RB, RA, u1s, u1t, u0s, u0t);
             }
         }
 

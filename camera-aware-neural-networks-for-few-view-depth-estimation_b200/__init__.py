@@ -63,7 +63,8 @@ ABI_SYMBOLS = (
     "cadl_stack_fwd_bwd", "cadl_stack_reduce", "cadl_stack_grad", "cadl_stats_offset", "cadl_stats_count",
     "cadl_si_fwd_bwd", "cadl_gradmatch_fwd_bwd", "cadl_smooth_fwd_bwd", "cadl_reproj_fwd_bwd",
     "cadl_scale_grad", "cadl_metrics", "cadl_rays_from_K", "cadl_photometric_fwd_bwd",
-    "cadl_batch_prep", "cadl_clip_workspace_bytes", "cadl_clip_grad_norm",
+    "cadl_batch_prep", "cadl_clip_workspace_bytes", "cadl_clip_grad_norm", "cadl_debug_set_trace",
+    "cadl_debug_kernel_times",
 )
 
 _lib = None
@@ -116,6 +117,8 @@ def lib() -> C.CDLL:
     L.cadl_clip_grad_norm.argtypes = [vp, vp, vp, C.c_int, C.c_longlong, C.c_float, f32p, vp, C.c_size_t, C.c_int, vp]
     L.cadl_debug_force_generic.argtypes = [C.c_int]
     L.cadl_debug_force_generic.restype = None
+    L.cadl_debug_set_trace.argtypes = [C.c_void_p, C.c_int]
+    L.cadl_debug_set_trace.restype = None
     L.cadl_selftest.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_float, vp, vp]
     for name in ABI_SYMBOLS:
         getattr(L, name)   # AttributeError here = the .so does not export what include/cadl.h declares
@@ -250,6 +253,27 @@ def force_generic(on):
     8 = the one-CTA-per-tile fast kernel instead of the streaming split (default for aligned shapes); with 8:
     2 = stage tiles with cp.async instead of TMA, 4 = warp-specialised persistent tile kernel."""
     lib().cadl_debug_force_generic(int(on))
+
+
+def kernel_times(enable: bool = True):
+    """Switch per-launch event timing of stack_fwd_bwd on/off; returns [(kernel, ms)] of the last timed call."""
+    L = lib()
+    L.cadl_debug_kernel_times.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.c_int]
+    L.cadl_debug_kernel_times.restype = C.c_int
+    ms = (C.c_float * 12)()
+    names = (C.c_char_p * 12)()
+    n = L.cadl_debug_kernel_times(int(enable), ms, names, 12)
+    return [(names[i].decode(), float(ms[i])) for i in range(n)]
+
+
+def set_trace(buf) -> None:
+    """Per-warp trace of the streaming phase-B kernel into an int64 CUDA tensor of shape (warps, 4):
+    {SM id, start ns, end ns, items}; None switches it off (profiles/trace_stream.py)."""
+    if buf is None:
+        lib().cadl_debug_set_trace(None, 0)
+    else:
+        assert buf.is_cuda and buf.dtype == torch.int64 and buf.is_contiguous() and buf.shape[1] == 4
+        lib().cadl_debug_set_trace(_ptr(buf), int(buf.shape[0]))
 
 
 def selftest(which: int, lo_bits: int, hi_bits: int, param: float = 0.0, device="cuda:0") -> int:

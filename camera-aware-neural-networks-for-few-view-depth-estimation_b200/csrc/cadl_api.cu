@@ -69,6 +69,7 @@ struct Ws {
     double* b_part() const { return reinterpret_cast<double*>(base + L.b_part); }
     double* img_sm() const { return reinterpret_cast<double*>(base + L.img_sm); }
     float* img_off() const { return reinterpret_cast<float*>(base + L.img_off); }
+    unsigned int* img_cnt() const { return reinterpret_cast<unsigned int*>(base + L.img_cnt); }
     bool has_pyr() const { return L.pyr_blocks > 0; }
     PyrArrays pyr() const {
         PyrArrays p;
@@ -83,7 +84,35 @@ struct Ws {
 };
 
 int g_force_generic = 0;
-int g_force_tile = 0;       // bit 3: the one-CTA-per-tile fast kernel instead of the streaming split
+int g_force_tile = 0;
+// cadl_debug_kernel_times: CUDA events between the launches of one cadl_stack_fwd_bwd call (debug / profiling aid)
+struct KTimes {
+    bool on = false;
+    int n = 0, n_last = 0;
+    cudaEvent_t ev[12] = {};
+    const char* name[12] = {};
+    const char* name_last[12] = {};
+    float ms_last[12] = {};
+};
+KTimes g_kt;
+void kt_mark(cudaStream_t st, const char* name) {
+    if (!g_kt.on || g_kt.n >= 12) return;
+    if (!g_kt.ev[g_kt.n]) cudaEventCreate(&g_kt.ev[g_kt.n]);
+    cudaEventRecord(g_kt.ev[g_kt.n], st);
+    g_kt.name[g_kt.n++] = name;
+}
+void kt_finish() {
+    if (!g_kt.on || g_kt.n < 2) return;
+    cudaEventSynchronize(g_kt.ev[g_kt.n - 1]);
+    g_kt.n_last = g_kt.n - 1;
+    for (int i = 1; i < g_kt.n; ++i) {
+        cudaEventElapsedTime(&g_kt.ms_last[i - 1], g_kt.ev[i - 1], g_kt.ev[i]);
+        g_kt.name_last[i - 1] = g_kt.name[i];
+    }
+    g_kt.n = 0;
+}
+unsigned long long* g_trace = nullptr;   // cadl_debug_set_trace
+int g_trace_cap = 0;       // bit 3: the one-CTA-per-tile fast kernel instead of the streaming split
 int g_force_no_tma = 0;
 int g_use_ws = 0;           // bit 2: warp-specialised persistent kernel instead of the plain one-tile-per-CTA fast kernel     // bit 1 of cadl_debug_force_generic: keep the fast kernel but stage with cp.async   // cadl_debug_force_generic(): tests compare the two phase-B kernels
 
@@ -228,24 +257,54 @@ cudaError_t launch_fast(PhaseBArgs& a, cudaStream_t st) {
 
 // streaming split of the fast path: pooled pyramid -> coarse coefficients -> full-resolution pass (cadl_phase_b_stream.cuh)
 template <int F>
-cudaError_t launch_stream(PhaseBArgs& a, const Ws& ws, cudaStream_t st) {
+cudaError_t launch_stream(PhaseBArgs& a, const Ws& ws, cudaStream_t st, bool* offset_done) {
     const PyrArrays py = ws.pyr();
-    const int nblk = ws.L.pyr_blocks, wpi = ws.L.wpi;
-    pyr_pool_kernel<<<nblk, 256, 0, st>>>(a.pred, a.gt, a.B, a.H, a.W, a.eps_grad, py);
+    const int nblk = ws.L.pyr_blocks;
+    pyr_pool_kernel<<<nblk, 256, 0, st>>>(a.pred, a.gt, a.B, a.H, a.W, a.eps_grad, py, ws.img_cnt());
+    kt_mark(st, "pyr_pool_kernel");
     PyrCoefArgs ca{};
     ca.py = py; ca.B = a.B; ca.H = a.H; ca.W = a.W;
     for (int s = 0; s < 4; ++s) { ca.inv_nx[s] = a.inv_nx[s]; ca.inv_ny[s] = a.inv_ny[s]; }
     ca.wg = 0.25f * a.w_grad * a.upstream;          // 1/num_scales * weight * upstream
-    ca.b_part = a.b_part; ca.row0 = a.B * wpi;
+    ca.b_part = a.b_part; ca.row0 = a.B;             // final rows: [B per-image rows][nblk rows of this kernel]
     pyr_coef_kernel<<<nblk, 256, 0, st>>>(ca);
+    kt_mark(st, "pyr_coef_kernel");
     StreamArgs sa{};
-    sa.c1 = py.c1; sa.wpi = wpi; sa.nstrip = (a.W + 127) / 128;
-    a.tiles_x = wpi; a.tiles_y = 1;                  // finalize_results: partial rows per image
-    a.b_rows = a.B * wpi + nblk;
-    sa.rows_total = a.b_rows;
-    const int grid = (a.B * wpi + kThreadsB / 32 - 1) / (kThreadsB / 32);
+    sa.c1 = py.c1; sa.nstrip = (a.W + 127) / 128;
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int wave = 2 * num_sms * (kThreadsB / 32);                 // resident warps: 2 CTAs x 8 warps per SM (128 registers)
+    const int SR = sa.nstrip * a.H;
+    sa.cpi = wave / a.B > 0 ? wave / a.B : 1;
+    if (sa.cpi > ws.L.stream_cpi) sa.cpi = ws.L.stream_cpi;         // workspace sized for this many rows per image
+    if (sa.cpi > SR) sa.cpi = SR;
+    sa.chunk_part = a.b_part + (size_t)(a.B + nblk) * BF_COUNT;
+    sa.img_cnt = ws.img_cnt();
+    a.tiles_x = 1; a.tiles_y = 1;                    // finalize_results: one (already reduced) row per image
+    a.b_rows = a.B + nblk;
+    sa.trace = g_trace; sa.trace_cap = g_trace_cap;
+    const bool defer = (F & FB_SMOOTH) && a.grad;    // results + offset in stream_finish_kernel
+    sa.finalize_inline = defer ? 0 : 1;
+    int grid = (a.B * sa.cpi + kThreadsB / 32 - 1) / (kThreadsB / 32);
+    if (grid > 2 * num_sms) grid = 2 * num_sms;
     if (a.mask) phase_b_stream_kernel<F, true><<<grid, kThreadsB, 0, st>>>(a, sa);
     else phase_b_stream_kernel<F, false><<<grid, kThreadsB, 0, st>>>(a, sa);
+    kt_mark(st, "phase_b_stream_kernel");
+    if (defer) {
+        const int HW = a.H * a.W;
+        const int vec = (HW % 4 == 0) && aligned(a.grad, 16);
+        int bx = (HW / 4 + 255) / 256;
+        int cap = (148 * 8 + a.B - 1) / a.B;
+        if (bx > cap) bx = cap;
+        if (bx < 1) bx = 1;
+        stream_finish_kernel<<<dim3(bx, a.B + 1), 256, 0, st>>>(a, vec);
+        kt_mark(st, "stream_finish_kernel");
+        *offset_done = true;
+    }
     return cudaGetLastError();
 }
 
@@ -341,6 +400,7 @@ int run_grad(const float* pred, const float* gt, const float* rgb, const float* 
     a.sm_ny = a.inv_ny[0];
 
     cudaError_t e = cudaSuccess;
+    bool offset_done = false;
     if ((t & (CADL_TERM_GRAD | CADL_TERM_SMOOTH)) == 0) {
         a.b_rows = kPointBlocks;
         const bool pfast = a.vec_ok && p.eps_si > 0.f && p.eps_si <= 1000.f && !g_force_generic;
@@ -370,9 +430,9 @@ int run_grad(const float* pred, const float* gt, const float* rgb, const float* 
         a.b_rows = a.tiles_x * a.tiles_y * B;
         const bool stream = (t & CADL_TERM_GRAD) && ws.has_pyr() && !g_force_tile;
         switch (t) {
-            case CADL_TERM_ALL: e = stream ? launch_stream<15>(a, ws, st) : launch_fast<15>(a, st); break;
-            case CADL_TERM_SI | CADL_TERM_GRAD | CADL_TERM_SMOOTH: e = stream ? launch_stream<7>(a, ws, st) : launch_fast<7>(a, st); break;
-            case CADL_TERM_GRAD: e = stream ? launch_stream<FB_GRAD>(a, ws, st) : launch_fast<FB_GRAD>(a, st); break;
+            case CADL_TERM_ALL: e = stream ? launch_stream<15>(a, ws, st, &offset_done) : launch_fast<15>(a, st); break;
+            case CADL_TERM_SI | CADL_TERM_GRAD | CADL_TERM_SMOOTH: e = stream ? launch_stream<7>(a, ws, st, &offset_done) : launch_fast<7>(a, st); break;
+            case CADL_TERM_GRAD: e = stream ? launch_stream<FB_GRAD>(a, ws, st, &offset_done) : launch_fast<FB_GRAD>(a, st); break;
             case CADL_TERM_SMOOTH: e = launch_fast<FB_SMOOTH>(a, st); break;
             default: return CADL_ERR_UNSUPPORTED;
         }
@@ -387,7 +447,7 @@ int run_grad(const float* pred, const float* gt, const float* rgb, const float* 
     }
     }
     if (e != cudaSuccess) return cuda_rc(e);
-    if ((t & CADL_TERM_SMOOTH) && grad) {
+    if ((t & CADL_TERM_SMOOTH) && grad && !offset_done) {
         const int HW = H * W;
         const int vec = (HW % 4 == 0) && aligned(grad, 16);
         int bx = (HW / 4 + 255) / 256;
@@ -395,6 +455,7 @@ int run_grad(const float* pred, const float* gt, const float* rgb, const float* 
         if (bx > cap) bx = cap;
         if (bx < 1) bx = 1;
         smooth_offset_kernel<<<dim3(bx, B), 256, 0, st>>>(grad, ws.img_off(), HW, vec);
+        kt_mark(st, "smooth_offset_kernel");
         e = cudaGetLastError();
     }
     return cuda_rc(e);
@@ -419,6 +480,22 @@ void cadl_default_params(cadl_params* p) {
 }
 
 int cadl_version(void) { return CADL_VERSION; }
+int cadl_debug_kernel_times(int enable, float* ms_out, const char** names_out, int cap) {
+    g_kt.on = enable != 0;
+    g_kt.n = 0;
+    int n = g_kt.n_last < cap ? g_kt.n_last : cap;
+    for (int i = 0; i < n; ++i) {
+        if (ms_out) ms_out[i] = g_kt.ms_last[i];
+        if (names_out) names_out[i] = g_kt.name_last[i];
+    }
+    return n;
+}
+
+void cadl_debug_set_trace(unsigned long long* dev_buf, int capacity_warps) {
+    g_trace = dev_buf;
+    g_trace_cap = dev_buf ? capacity_warps : 0;
+}
+
 void cadl_debug_force_generic(int on) {
     g_force_generic = on & 1;
     g_force_no_tma = (on >> 1) & 1;
@@ -493,9 +570,14 @@ int cadl_stack_fwd_bwd(const float* pred, const float* gt, const float* rgb, con
     int rc = check_common(B, H, W, workspace, workspace_bytes);
     if (rc) return rc;
     Ws ws = make_ws(workspace, B, H, W);
+    kt_mark((cudaStream_t)stream, "start");
     rc = run_reduce(pred, gt, mask, B, H, W, *params, ws, (cudaStream_t)stream);
     if (rc) return rc;
-    return run_grad(pred, gt, rgb, K, mask, B, H, W, *params, grad_pred, results, ws, (cudaStream_t)stream);
+    kt_mark((cudaStream_t)stream, "phase_a_kernel");
+    rc = run_grad(pred, gt, rgb, K, mask, B, H, W, *params, grad_pred, results, ws, (cudaStream_t)stream);
+    kt_mark((cudaStream_t)stream, "end");
+    kt_finish();
+    return rc;
 }
 
 int cadl_si_fwd_bwd(const float* pred, const float* gt, const uint8_t* mask, int B, int H, int W, float lambda,

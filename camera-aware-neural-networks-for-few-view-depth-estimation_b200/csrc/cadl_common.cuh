@@ -52,15 +52,15 @@ struct WsHeader {
 };
 
 struct WsLayout {
-    size_t header, stats, img_psum, a_part, b_part, img_sm, img_off, total;
+    size_t header, stats, img_psum, a_part, b_part, img_sm, img_off, img_cnt, total;
     size_t pyr_lp[3], pyr_lg[3], pyr_rq[3], pyr_c1;   // streaming fast path (cadl_phase_b_stream.cuh); 0 = absent
     int a_blocks_per_img, a_blocks, b_tiles;
-    int wpi;          // streaming kernel: warps per image (one wave of 148 SMs x 16 warps over the batch)
+    int stream_cpi;   // streaming kernel: static shares per image (one per warp of the resident wave)
     int pyr_blocks;   // CTAs of pyr_pool_kernel / pyr_coef_kernel (0: shape not a multiple of 8)
 };
 
 constexpr int kPointBlocks = 148 * 8;       // partial rows of the pointwise kernels
-constexpr int kStreamWarps = 148 * 16;      // resident warps of phase_b_stream_kernel (128 registers, 2 CTAs x 8 warps per SM)
+constexpr int kStreamWaveWarps = 160 * 16;  // upper bound of the streaming kernel's resident warps (2 CTAs x 8 warps x <=160 SMs)
 
 constexpr int kThreadsA = 256;
 constexpr int kThreadsB = 256;
@@ -73,7 +73,7 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 __host__ inline int a_blocks_per_image(int B, int HW) {
     // ~4 resident blocks per SM over 148 SMs in one wave (fat threads amortise the block-end reduction),
     // at least 1024 px per block, each block inside one image
-    int target = (148 * 4 + B - 1) / B;
+    int target = (148 * 4) / B;          // rounded DOWN: one block too many per image starts a second, almost empty wave
     if (target < 1) target = 1;
     int by_size = (HW + 1023) / 1024;
     int n = target < by_size ? target : by_size;
@@ -92,15 +92,18 @@ __host__ inline WsLayout ws_layout(int B, int H, int W) {
     L.stats = o;    o = align_up(o + sizeof(double) * ST_COUNT, 256);
     L.img_psum = o; o = align_up(o + sizeof(double) * B, 256);
     L.a_part = o;   o = align_up(o + sizeof(double) * (size_t)L.a_blocks * AF_COUNT, 256);
-    L.wpi = kStreamWarps / B > 0 ? kStreamWarps / B : 1;
+    L.stream_cpi = kStreamWaveWarps / B > 0 ? kStreamWaveWarps / B : 1;
     const bool pyr = (H % 8 == 0) && (W % 8 == 0);
     L.pyr_blocks = pyr ? (int)(((size_t)B * (H / 8) * (W / 8) + 255) / 256) : 0;
     size_t b_rows = (size_t)L.b_tiles;
     if (b_rows < (size_t)kPointBlocks) b_rows = kPointBlocks;
-    if (pyr && b_rows < (size_t)B * L.wpi + L.pyr_blocks) b_rows = (size_t)B * L.wpi + L.pyr_blocks;
+    // streaming path: [B per-image rows][pyr_coef_kernel rows][one row per chunk]
+    if (pyr && b_rows < (size_t)B + L.pyr_blocks + (size_t)B * L.stream_cpi)
+        b_rows = (size_t)B + L.pyr_blocks + (size_t)B * L.stream_cpi;
     L.b_part = o;   o = align_up(o + sizeof(double) * b_rows * BF_COUNT, 256);
     L.img_sm = o;   o = align_up(o + sizeof(double) * (size_t)B * 2, 256);
     L.img_off = o;  o = align_up(o + sizeof(float) * (size_t)B, 256);
+    L.img_cnt = o;  o = align_up(o + sizeof(unsigned int) * (size_t)B, 256);   // chunks done per image (streaming kernel)
     for (int s = 0; s < 3; ++s) {
         const size_t cells = pyr ? (size_t)B * (H >> (s + 1)) * (W >> (s + 1)) : 0;
         L.pyr_lp[s] = pyr ? o : 0; o = align_up(o + sizeof(float) * cells, 256);

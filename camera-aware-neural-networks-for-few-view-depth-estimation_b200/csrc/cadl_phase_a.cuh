@@ -295,17 +295,49 @@ __global__ void __launch_bounds__(kThreadsA, 4) phase_a_kernel(const PhaseAArgs 
     __threadfence();
 
     const int nblk = a.B * a.blocks_per_img;
-    const volatile double* part = a.a_part;
-    // one warp per quantity (fixed lane-strided order + fixed shuffle tree: deterministic), no block barriers
-    for (int q = warp; q < AF_COUNT; q += kThreadsA / 32) {
-        if (q == AF_PSUM) continue;
-        if (!(F & FA_SI) && (q == AF_SI_S || q == AF_SI_Q)) continue;
-        if (!(F & FA_EV) && q >= AF_EV_ABSREL && q <= AF_EV_SUMG) continue;
-        if (!(F & FA_TR) && q >= AF_TR_ABSREL && q <= AF_TR_LOGSQ) continue;
-        double acc = 0.0;
-        for (int i = lane; i < nblk; i += 32) acc += part[(size_t)i * AF_COUNT + q];
-        const double r = warp_sum(acc);
-        if (lane == 0) {
+    const double* part = a.a_part;
+    // One partial row per thread and trip, two halves of the quantities (register budget): every load of a trip is
+    // independent -- a dependent chain of L2 round trips per quantity cost ~15 us.  Fixed thread-strided order,
+    // fixed shuffle tree, fixed warp order: deterministic.  __ldcg: rows written by other SMs (fence + ticket).
+    __shared__ double s_wa[kThreadsA / 32][AF_COUNT];
+    constexpr int kHalf = (AF_COUNT + 1) / 2;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        double accq[kHalf];
+#pragma unroll
+        for (int q = 0; q < kHalf; ++q) accq[q] = 0.0;
+        for (int i = tid; i < nblk; i += 3 * kThreadsA) {       // three rows per trip: 24 independent loads in flight
+            const int i2 = i + kThreadsA, i3 = i + 2 * kThreadsA;
+            double r0[kHalf], r1[kHalf], r2[kHalf];
+#pragma unroll
+            for (int q = 0; q < kHalf; ++q) {
+                const bool on = h * kHalf + q < AF_COUNT;
+                r0[q] = on ? __ldcg(part + (size_t)i * AF_COUNT + h * kHalf + q) : 0.0;
+                r1[q] = (on && i2 < nblk) ? __ldcg(part + (size_t)i2 * AF_COUNT + h * kHalf + q) : 0.0;
+                r2[q] = (on && i3 < nblk) ? __ldcg(part + (size_t)i3 * AF_COUNT + h * kHalf + q) : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < kHalf; ++q) accq[q] = ((accq[q] + r0[q]) + r1[q]) + r2[q];
+        }
+#pragma unroll
+        for (int q = 0; q < kHalf; ++q) {
+            if (h * kHalf + q < AF_COUNT) {
+                const double v = warp_sum(accq[q]);
+                if (lane == 0) s_wa[warp][h * kHalf + q] = v;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < AF_COUNT) {
+        const int q = tid;
+        bool on = q != AF_PSUM;
+        if (!(F & FA_SI) && (q == AF_SI_S || q == AF_SI_Q)) on = false;
+        if (!(F & FA_EV) && q >= AF_EV_ABSREL && q <= AF_EV_SUMG) on = false;
+        if (!(F & FA_TR) && q >= AF_TR_ABSREL && q <= AF_TR_LOGSQ) on = false;
+        if (on) {
+            double r = 0.0;
+#pragma unroll
+            for (int w = 0; w < kThreadsA / 32; ++w) r += s_wa[w][q];
             int st = -1;
             switch (q) {
                 case AF_SI_S: st = ST_SI_S; break;
@@ -331,8 +363,9 @@ __global__ void __launch_bounds__(kThreadsA, 4) phase_a_kernel(const PhaseAArgs 
     if constexpr (F & FA_PSUM)
     for (int img = warp; img < a.B; img += kThreadsA / 32) {
         double acc = 0.0;
+#pragma unroll 4
         for (int i = lane; i < a.blocks_per_img; i += 32)
-            acc += part[((size_t)img * a.blocks_per_img + i) * AF_COUNT + AF_PSUM];
+            acc += __ldcg(part + ((size_t)img * a.blocks_per_img + i) * AF_COUNT + AF_PSUM);
         acc = warp_sum(acc);
         if (lane == 0) a.img_psum[img] = acc;
     }

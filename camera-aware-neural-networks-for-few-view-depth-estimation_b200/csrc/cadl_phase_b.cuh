@@ -119,76 +119,132 @@ __device__ __forceinline__ void scale_dims(const PhaseBArgs& a, int s, int& Hs, 
     inv_ny = ny > 0.0 ? (float)(1.0 / ny) : 0.f;
 }
 
-// Final reduction + results, executed by the last CTA of phase B (all threads of the block).
+// Image b's share of the smoothness loss and the constant its gradient is shifted by:
+//   L_b = a_b * (sum_x / n_x + sum_y / n_y),   a_b = 1 / (mean(pred_b) + eps)          depth_loss.h:192-193, :230-231
+//   d/dp_j of the mean-normalisation = -a_b * L_b / (H*W)
+__device__ __forceinline__ void smooth_image_share(const PhaseBArgs& a, int img, double sx, double sy, double& Lb, float& off) {
+    const double HW = (double)a.H * a.W;
+    const double nx = (double)a.global_B * a.H * (a.W - 1);
+    const double ny = (double)a.global_B * (a.H - 1) * a.W;
+    const double mean = a.img_psum[img] / HW;
+    const float ab = 1.0f / ((float)mean + a.eps_smooth);   // depth_loss.h:193
+    Lb = (double)ab * (sx / nx + sy / ny);
+    off = (float)((double)a.upstream * a.w_smooth * ab * Lb / HW);
+}
+
+// Final reduction + results, executed by ONE CTA (all of its threads, >= 64) after every partial row is visible.
+// Written as a short dependency chain -- one round of independent global loads, block reductions, six result
+// terms on six threads, one writer -- because it runs with the rest of the GPU idle or waiting (the first version,
+// a lane-strided dependent load loop per quantity and one thread doing every division, took 20-30 us).
+// Deterministic: fixed thread-strided order, fixed shuffle tree, fixed warp order.
 __device__ void finalize_results(const PhaseBArgs& a, double* s_d) {
-    const int tid = threadIdx.x;
-    const volatile double* part = a.b_part;
-    __shared__ double s_tot[BF_COUNT];
-    {   // one warp per quantity: fixed lane-strided order + fixed shuffle tree (deterministic), no block barriers
-        const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
-        for (int q = warp; q < BF_COUNT; q += nwarp) {
-            if (q == BF_SMX || q == BF_SMY) continue;
-            double acc = 0.0;
-            for (int i = lane; i < a.b_rows; i += 32) acc += part[(size_t)i * BF_COUNT + q];
-            acc = warp_sum(acc);
-            if (lane == 0) s_tot[q] = acc;
+    (void)s_d;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+    const double* part = a.b_part;
+    constexpr int NQ = BF_COUNT + 1;                 // + the a_b-weighted smoothness total
+    __shared__ double s_w[32][NQ];
+    __shared__ double s_tot[NQ];
+    __shared__ double s_term[4 + 2];
+    const bool smooth = (a.terms & CADL_TERM_SMOOTH) != 0;
+    const int tpi = a.tiles_x * a.tiles_y;
+
+    // ---- 1. global loads: partial rows (three per thread and trip), per-image smoothness shares ----
+    double accq[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) accq[q] = 0.0;
+    for (int i = tid; i < a.b_rows; i += 3 * blockDim.x) {
+        const int i2 = i + blockDim.x, i3 = i + 2 * blockDim.x;
+        double r0[BF_COUNT], r1[BF_COUNT], r2[BF_COUNT];
+#pragma unroll
+        for (int q = 0; q < BF_COUNT; ++q) {      // __ldcg: written by other SMs, never cached in this L1
+            r0[q] = __ldcg(part + (size_t)i * BF_COUNT + q);
+            r1[q] = i2 < a.b_rows ? __ldcg(part + (size_t)i2 * BF_COUNT + q) : 0.0;
+            r2[q] = i3 < a.b_rows ? __ldcg(part + (size_t)i3 * BF_COUNT + q) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < BF_COUNT; ++q) accq[q] = ((accq[q] + r0[q]) + r1[q]) + r2[q];
+    }
+    if (smooth) {
+        // per-image sums (the partial rows of an image are contiguous), then a_b-weighted
+        if (tpi == 1) {   // rows already folded per image (streaming kernel): one thread per image
+            for (int img = tid; img < a.B; img += blockDim.x) {
+                double Lb;
+                float off;
+                smooth_image_share(a, img, __ldcg(part + (size_t)img * BF_COUNT + BF_SMX),
+                                   __ldcg(part + (size_t)img * BF_COUNT + BF_SMY), Lb, off);
+                a.img_sm[2 * img] = Lb;
+                a.img_off[img] = off;
+                accq[BF_COUNT] += Lb;
+            }
+        } else {
+            for (int img = warp; img < a.B; img += nwarp) {
+                double sx = 0.0, sy = 0.0;
+#pragma unroll 4
+                for (int i = lane; i < tpi; i += 32) {
+                    sx += __ldcg(part + ((size_t)img * tpi + i) * BF_COUNT + BF_SMX);
+                    sy += __ldcg(part + ((size_t)img * tpi + i) * BF_COUNT + BF_SMY);
+                }
+                sx = warp_sum(sx);
+                sy = warp_sum(sy);
+                if (lane == 0) {
+                    double Lb;
+                    float off;
+                    smooth_image_share(a, img, sx, sy, Lb, off);
+                    a.img_sm[2 * img] = Lb;
+                    a.img_off[img] = off;
+                    accq[BF_COUNT] += Lb;
+                }
+            }
         }
     }
-    // smoothness: per-image sums (tiles of an image are contiguous rows), then a_b-weighted total
-    double sm_acc = 0.0;
-    if (a.terms & CADL_TERM_SMOOTH) {
-        const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
-        const int tpi = a.tiles_x * a.tiles_y;
-        const double HW = (double)a.H * a.W;
-        const double nx = (double)a.global_B * a.H * (a.W - 1);
-        const double ny = (double)a.global_B * (a.H - 1) * a.W;
-        for (int img = warp; img < a.B; img += nwarp) {
-            double sx = 0.0, sy = 0.0;
-            for (int i = lane; i < tpi; i += 32) {
-                sx += part[((size_t)img * tpi + i) * BF_COUNT + BF_SMX];
-                sy += part[((size_t)img * tpi + i) * BF_COUNT + BF_SMY];
-            }
-            sx = warp_sum(sx);
-            sy = warp_sum(sy);
-            if (lane == 0) {
-                double mean = a.img_psum[img] / HW;
-                float ab = 1.0f / ((float)mean + a.eps_smooth);   // depth_loss.h:193
-                double Lb = (double)ab * (sx / nx + sy / ny);     // image b's share of the loss
-                a.img_sm[2 * img] = Lb;
-                // d/dp_j of the mean-normalisation: -a_b * L_b / (H*W)   
-                a.img_off[img] = (float)((double)a.upstream * a.w_smooth * ab * Lb / HW);
-            }
+    // ---- 2. block reduction ----
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const double v = warp_sum(accq[q]);
+        if (lane == 0) s_w[warp][q] = v;
+    }
+    __syncthreads();
+    if (tid < NQ) {
+        double t = 0.0;
+        for (int w = 0; w < nwarp; ++w) t += s_w[w][tid];
+        s_tot[tid] = t;
+    }
+    __syncthreads();
+    // ---- 3. the result terms, one thread each ----
+    const double* st = a.stats;
+    if (tid < 4) {            // gradient matching, scale tid                       depth_loss.h:162-163
+        double term = 0.0;
+        if ((a.terms & CADL_TERM_GRAD) && tid < a.num_scales) {
+            const int Hs = a.H >> tid, Ws = a.W >> tid;
+            const double nx = (double)a.global_B * Hs * (Ws - 1);
+            const double ny = (double)a.global_B * (Hs - 1) * Ws;
+            term = s_tot[BF_GX0 + 2 * tid] / nx + s_tot[BF_GY0 + 2 * tid] / ny;
         }
-        __syncthreads();
-        double v = 0.0;
-        for (int i = tid; i < a.B; i += blockDim.x) v += ((const volatile double*)a.img_sm)[2 * i];
-        sm_acc = block_sum_double(v, s_d);
+        s_term[tid] = term;
+    } else if (tid == 32) {   // scale-invariant                                      depth_loss.h:58-63
+        double si = 0.0;
+        if (a.terms & CADL_TERM_SI) {
+            const double n = st[ST_SI_N];
+            if (n > 0.0) si = st[ST_SI_Q] / n - (double)a.lambda * st[ST_SI_S] * st[ST_SI_S] / (n * n);
+        }
+        s_term[4] = si;
+    } else if (tid == 33) {   // reprojection                                         depth_loss.h:323-330
+        double rp = 0.0;
+        if (a.terms & CADL_TERM_REPROJ) {
+            const double n = st[ST_RP_N];
+            if (n > 0.0) rp = s_tot[BF_RP_E] / n;
+        }
+        s_term[5] = rp;
     }
     __syncthreads();
     if (tid == 0) {
         cadl_results& r = *a.results;
-        const double* st = a.stats;
-        double si = 0.0, gm = 0.0, sm = 0.0, rp = 0.0;
-        if (a.terms & CADL_TERM_SI) {
-            double n = st[ST_SI_N];
-            if (n > 0.0) si = st[ST_SI_Q] / n - (double)a.lambda * st[ST_SI_S] * st[ST_SI_S] / (n * n);
-            r.n_si = (int64_t)n;
-        } else r.n_si = 0;
-        if (a.terms & CADL_TERM_GRAD) {
-            for (int s = 0; s < a.num_scales; ++s) {
-                int Hs = a.H >> s, Ws = a.W >> s;
-                double nx = (double)a.global_B * Hs * (Ws - 1);
-                double ny = (double)a.global_B * (Hs - 1) * Ws;
-                gm += s_tot[BF_GX0 + 2 * s] / nx + s_tot[BF_GY0 + 2 * s] / ny;
-            }
-            gm /= (double)a.num_scales;
-        }
-        if (a.terms & CADL_TERM_SMOOTH) sm = sm_acc;
-        if (a.terms & CADL_TERM_REPROJ) {
-            double n = st[ST_RP_N];
-            if (n > 0.0) rp = s_tot[BF_RP_E] / n;
-            r.n_reproj = (int64_t)n;
-        } else r.n_reproj = 0;
+        double gm = 0.0;
+        for (int s = 0; s < a.num_scales; ++s) gm += s_term[s];
+        gm = (a.terms & CADL_TERM_GRAD) ? gm / (double)a.num_scales : 0.0;
+        const double si = s_term[4], rp = s_term[5], sm = smooth ? s_tot[BF_COUNT] : 0.0;
+        r.n_si = (a.terms & CADL_TERM_SI) ? (int64_t)st[ST_SI_N] : 0;
+        r.n_reproj = (a.terms & CADL_TERM_REPROJ) ? (int64_t)st[ST_RP_N] : 0;
         r.d_si = si; r.d_grad = gm; r.d_smooth = sm; r.d_reproj = rp;
         r.loss_si = (float)si; r.loss_grad = (float)gm; r.loss_smooth = (float)sm; r.loss_reproj = (float)rp;
         // depth_loss.h:427-430, in float like the reference's tensor arithmetic
@@ -203,45 +259,41 @@ __device__ void finalize_results(const PhaseBArgs& a, double* s_d) {
     }
 }
 
-// Metrics results from the phase-A statistics (depth_metrics.h:69-85; trainer :418-436).
-__device__ inline void write_metric_results(const double* st, uint32_t which, cadl_results& r) {
+// Metrics results from the phase-A statistics (depth_metrics.h:69-85; trainer :418-436).  Called by at least 32
+// threads with t = thread index: one value per thread (a single thread doing the ~25 double divisions one after
+// the other was ~4 us of serial tail).
+__device__ inline void write_metric_results(const double* st, uint32_t which, cadl_results& r, int t) {
     if (which & CADL_METRICS_EVAL) {
-        double n = st[ST_EV_N];
-        for (int i = 0; i < 12; ++i) r.eval[i] = 0.f;   // getZeroMetrics, depth_metrics.h:238-253
-        r.eval_counts[0] = (int64_t)n;
-        r.eval_counts[1] = (int64_t)st[ST_EV_C1];
-        r.eval_counts[2] = (int64_t)st[ST_EV_C2];
-        r.eval_counts[3] = (int64_t)st[ST_EV_C3];
-        if (n > 0.0) {
-            r.eval[0] = (float)(st[ST_EV_ABSREL] / n);
-            r.eval[1] = (float)(st[ST_EV_SQREL] / n);
-            r.eval[2] = sqrtf((float)(st[ST_EV_SQ] / n));
-            r.eval[3] = sqrtf((float)(st[ST_EV_LOGSQ] / n));
-            r.eval[4] = (float)(st[ST_EV_ABS] / n);
-            r.eval[5] = (float)(st[ST_EV_LOG10] / n);
-            r.eval[6] = (float)(st[ST_EV_C1] / n);
-            r.eval[7] = (float)(st[ST_EV_C2] / n);
-            r.eval[8] = (float)(st[ST_EV_C3] / n);
-            r.eval[9] = (float)n;                        // static_cast<float>(num_valid), :83
-            r.eval[10] = (float)(st[ST_EV_SUMP] / n);
-            r.eval[11] = (float)(st[ST_EV_SUMG] / n);
+        const double n = st[ST_EV_N];
+        if (t < 12) {
+            // getZeroMetrics when nothing is valid, depth_metrics.h:238-253
+            const int src = t == 0 ? ST_EV_ABSREL : t == 1 ? ST_EV_SQREL : t == 2 ? ST_EV_SQ : t == 3 ? ST_EV_LOGSQ
+                          : t == 4 ? ST_EV_ABS : t == 5 ? ST_EV_LOG10 : t == 6 ? ST_EV_C1 : t == 7 ? ST_EV_C2
+                          : t == 8 ? ST_EV_C3 : t == 10 ? ST_EV_SUMP : ST_EV_SUMG;
+            float v = 0.f;
+            if (n > 0.0) {
+                if (t == 9) v = (float)n;                                  // static_cast<float>(num_valid), :83
+                else if (t == 2 || t == 3) v = sqrtf((float)(st[src] / n));
+                else v = (float)(st[src] / n);
+            }
+            r.eval[t] = v;
+        } else if (t < 16) {
+            const int k = t - 12;
+            r.eval_counts[k] = (int64_t)st[k == 0 ? ST_EV_N : ST_EV_C1 + (k - 1)];
         }
     }
     if (which & CADL_METRICS_TRAIN) {
-        double n = st[ST_TR_N];
-        for (int i = 0; i < 8; ++i) r.train[i] = 0.f;
-        r.train_counts[0] = (int64_t)n;
-        r.train_counts[1] = (int64_t)st[ST_TR_C1];
-        r.train_counts[2] = (int64_t)st[ST_TR_C2];
-        r.train_counts[3] = (int64_t)st[ST_TR_C3];
-        if (n > 0.0) {
-            r.train[0] = (float)(st[ST_TR_ABSREL] / n);
-            r.train[1] = (float)(st[ST_TR_SQREL] / n);
-            r.train[2] = sqrtf((float)(st[ST_TR_SQ] / n));
-            r.train[3] = sqrtf((float)(st[ST_TR_LOGSQ] / n));
-            r.train[4] = (float)(st[ST_TR_C1] / n);
-            r.train[5] = (float)(st[ST_TR_C2] / n);
-            r.train[6] = (float)(st[ST_TR_C3] / n);
+        const double n = st[ST_TR_N];
+        if (t >= 16 && t < 24) {
+            const int k = t - 16;
+            const int src = k == 0 ? ST_TR_ABSREL : k == 1 ? ST_TR_SQREL : k == 2 ? ST_TR_SQ : k == 3 ? ST_TR_LOGSQ
+                          : k == 4 ? ST_TR_C1 : k == 5 ? ST_TR_C2 : ST_TR_C3;
+            float v = 0.f;
+            if (n > 0.0 && k < 7) v = (k == 2 || k == 3) ? sqrtf((float)(st[src] / n)) : (float)(st[src] / n);
+            r.train[k] = v;
+        } else if (t >= 24 && t < 28) {
+            const int k = t - 24;
+            r.train_counts[k] = (int64_t)st[k == 0 ? ST_TR_N : ST_TR_C1 + (k - 1)];
         }
     }
 }
@@ -406,7 +458,7 @@ __global__ void __launch_bounds__(kThreadsB) phase_b_point_kernel(const PhaseBAr
     }
     if (publish_partials(a, acc, blockIdx.x, s_f, &s_last)) {
         finalize_results(a, s_d);
-        if (tid == 0 && a.metrics) write_metric_results(a.stats, a.metrics, *a.results);
+        if (a.metrics) write_metric_results(a.stats, a.metrics, *a.results, tid);
     }
 }
 
@@ -799,7 +851,7 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_tile_kernel(const PhaseB
 
     if (publish_partials(a, acc, tile, s_f, &s_last)) {
         finalize_results(a, s_d);
-        if (tid == 0 && a.metrics) write_metric_results(a.stats, a.metrics, *a.results);
+        if (a.metrics) write_metric_results(a.stats, a.metrics, *a.results, tid);
     }
 }
 
@@ -844,7 +896,7 @@ __global__ void __launch_bounds__(256) scale_grad_kernel(const float* in, const 
 
 // metrics-only finalisation (no loss terms requested)
 __global__ void metrics_finalize_kernel(const double* stats, uint32_t which, cadl_results* r) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) write_metric_results(stats, which, *r);
+    if (blockIdx.x == 0) write_metric_results(stats, which, *r, threadIdx.x);   // launched with 32 threads
 }
 
 }  // namespace cadl

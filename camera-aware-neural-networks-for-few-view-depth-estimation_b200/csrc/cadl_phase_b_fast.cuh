@@ -685,7 +685,7 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
 
     if (publish_partials(a, acc, tile, s_f, &s_last)) {
         finalize_results(a, s_d);
-        if (tid == 0 && a.metrics) write_metric_results(a.stats, a.metrics, *a.results);
+        if (a.metrics) write_metric_results(a.stats, a.metrics, *a.results, tid);
     }
 }
 
@@ -806,7 +806,7 @@ __global__ void __launch_bounds__(kThreadsB) phase_b_point_fast_kernel(const Pha
     }
     if (publish_partials(a, acc, blockIdx.y * gridDim.x + blockIdx.x, s_f, &s_last)) {
         finalize_results(a, s_d);
-        if (tid == 0 && a.metrics) write_metric_results(a.stats, a.metrics, *a.results);
+        if (a.metrics) write_metric_results(a.stats, a.metrics, *a.results, tid);
     }
 }
 

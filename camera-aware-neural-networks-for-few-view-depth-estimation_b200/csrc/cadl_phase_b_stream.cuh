@@ -16,8 +16,12 @@
 //                     2x2 cell adds to its gradient; loss sums of the three coarse scales
 //   phase_b_stream_kernel   the full-resolution pass alone: one warp = 128 columns marching down ~32 rows, logs
 //                     evaluated in registers as each row arrives, every edge once, no shared memory, no barriers,
-//                     no halo except one pixel per warp end.  The image's strip-rows are divided evenly over the
-//                     warps of ONE wave (148 SMs x 16 warps), so there is no tail.
+//                     no halo except one pixel per warp end.  Each image's strip-rows are divided evenly over the
+//                     warps of ONE resident wave (2 CTAs x 8 warps per SM), so there is no tail of partial waves
+//                     (claiming 8-row chunks dynamically was measured slower: +10 % instructions for the extra
+//                     prologues and a tail of up to one chunk out of four).  The warp that finishes an image folds
+//                     that image's partial rows into one, so the kernel-final reduction reads B rows, not thousands
+//                     (a single CTA reading one row per warp was a 30 us serial tail).
 //
 // Values are the same as the tile kernel's (same operations on the sign-critical paths); tests compare the two.
 #pragma once
@@ -39,9 +43,14 @@ struct PyrArrays {
 // pyr_pool_kernel
 // ================================================================================================
 __global__ void __launch_bounds__(256) pyr_pool_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
-                                                       int B, int H, int W, float eps, PyrArrays py) {
+                                                       int B, int H, int W, float eps, PyrArrays py,
+                                                       unsigned int* img_cnt) {
     const int W8 = W >> 3, H8 = H >> 3;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    // the streaming kernel's per-image completion counters (stream-ordered before it; their offset depends on the
+    // shape, and one workspace serves calls of different shapes)
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < B; i += blockDim.x) img_cnt[i] = 0u;
     if (idx >= B * H8 * W8) return;
     const int bx = idx % W8, by = (idx / W8) % H8, b = idx / (W8 * H8);
     const float* pp = pred + (size_t)b * H * W + (size_t)(by * 8) * W + bx * 8;
@@ -246,10 +255,36 @@ __global__ void __launch_bounds__(256) pyr_coef_kernel(const PyrCoefArgs a) {
 // ================================================================================================
 struct StreamArgs {
     const float* c1;     // PyrArrays::c1
-    int wpi;             // warps per image
     int nstrip;          // 128-column strips per image row
-    int rows_total;      // partial rows finalize_results sums (B * wpi + rows of pyr_coef_kernel)
+    int cpi;             // shares per image (partial rows of an image are contiguous)
+    double* chunk_part;  // one partial row per share; a.b_part holds [B per-image rows][pyr rows]
+    unsigned int* img_cnt;   // shares done per image (zeroed by pyr_pool_kernel)
+    int finalize_inline; // 1: the last CTA reduces and writes cadl_results; 0: stream_finish_kernel does (smoothness + gradient)
+    unsigned long long* trace;   // cadl_debug_set_trace: per warp {smid, start ns, end ns, items}; null = off
+    int trace_cap;
 };
+constexpr int kStreamPrefetchRows = 3;     // L2 prefetch distance inside a chunk
+
+// Sum of one image's chunk rows in a fixed order (lane-strided, fixed shuffle tree), by the warp that finished the image.
+__device__ __noinline__ void fold_image_rows(const double* rows, int n, double* out, unsigned int* cnt, int lane) {
+    __threadfence();
+    double t[BF_COUNT];
+#pragma unroll
+    for (int q = 0; q < BF_COUNT; ++q) t[q] = 0.0;
+#pragma unroll 2
+    for (int i = lane; i < n; i += 32) {
+#pragma unroll
+        for (int q = 0; q < BF_COUNT; ++q) t[q] += __ldcg(rows + (size_t)i * BF_COUNT + q);
+    }
+    double mine = 0.0;
+#pragma unroll
+    for (int q = 0; q < BF_COUNT; ++q) {
+        const double r = warp_sum(t[q]);
+        mine = (lane == q) ? r : mine;
+    }
+    if (lane < BF_COUNT) out[lane] = mine;
+    if (lane == 0) *cnt = 0u;
+}
 
 // One image row as a lane holds it: its own 4 pixels, the right neighbour, and the end lanes' halo pixel.
 struct StreamRow {
@@ -267,58 +302,81 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_stream_kernel(const Phas
     constexpr bool SI = (F & FB_SI) != 0;
     constexpr bool RP = (F & FB_RP) != 0;
     static_assert((F & FB_GRAD) != 0, "the streaming kernel is the gradient-matching path");
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int H = a.H, W = a.W;
-    const int gw = blockIdx.x * (kThreadsB / 32) + warp;
-    const int b = gw / sa.wpi, wi = gw - b * sa.wpi;
+    const int plane = H * W, W1 = W >> 1;                    // 3*H*W < 2^31 (checked on the host)
+    const float up = a.upstream;
+    const float inx0 = a.inv_nx[0] * 0.25f * a.w_grad * up, iny0 = a.inv_ny[0] * 0.25f * a.w_grad * up;
+    const float eps_g = a.eps_grad, eps_r = a.eps_rp;
+    constexpr float kExpScale = -1.4426950408889634f / 3.0f;    // exp(-mean_c|dI|) = 2^(kExpScale * sum_c|dI|)
 
-    if (b < a.B) {
-        float acc[BF_COUNT];
-#pragma unroll
-        for (int q = 0; q < BF_COUNT; ++q) acc[q] = 0.f;
+    // scalars derived from the phase-A statistics, weights and upstream folded in
+    float c1 = 0.f, c2 = 0.f, rpn = 0.f;
+    {
+        const double n = a.stats[ST_SI_N], S = a.stats[ST_SI_S], nr = a.stats[ST_RP_N];
+        if (SI && n > 0.0) {
+            c1 = (float)(2.0 / n) * a.w_si * up;
+            c2 = (float)(-2.0 * (double)a.lambda * S / (n * n)) * a.w_si * up;
+        }
+        if (RP && nr > 0.0) rpn = (float)(1.0 / nr) * a.w_rp * up;
+    }
 
-        const int img = b * H * W;                               // B*H*W < 2^31 (checked on the host)
-        const float* __restrict__ predb = a.pred + img;
-        const float* __restrict__ gtb = a.gt + img;
-        const float* __restrict__ rgbb = SMOOTH ? a.rgb + (size_t)b * 3 * H * W : nullptr;
-        const float* __restrict__ c1b = sa.c1 + (size_t)b * (H >> 1) * (W >> 1);
-        float* __restrict__ gradb = a.grad ? a.grad + img : nullptr;
-        const int plane = H * W, W1 = W >> 1;                    // 3*H*W < 2^31 (checked on the host)
-        const float up = a.upstream;
+    // lanes 0..19 each own one 128-byte line of a 128-column row segment: pred, gt, 3 x rgb  x 4 lines
+    const int pf_t = lane >> 2, pf_seg = lane & 3;
+    auto prefetch_row = [&](int b, int strip, int y) {
+        const int x = strip * 128 + pf_seg * 32;
+        if (lane < (SMOOTH ? 20 : 8) && x < W) {
+            const float* base = pf_t == 0 ? a.pred + (size_t)b * plane
+                              : pf_t == 1 ? a.gt + (size_t)b * plane
+                                          : a.rgb + ((size_t)b * 3 + (pf_t - 2)) * plane;
+            prefetch_l2(base + (size_t)y * W + x);
+        }
+    };
 
-        // scalars derived from the phase-A statistics, weights and upstream folded in
-        float c1 = 0.f, c2 = 0.f, rpn = 0.f, abw = 0.f;
+    // Work items: every image's strip-rows (strip-major) cut into cpi equal shares, one per warp of the single
+    // resident wave (more than one per warp only for huge batches).  cadl_debug_set_trace shows warps finishing
+    // within +-12 % of each other; handing the last quarter of each image out dynamically in 4-row chunks was
+    // measured SLOWER (114 vs 104 us: every chunk restarts the two-row prologue with its loads exposed).
+    const int nwarps = gridDim.x * (kThreadsB / 32);
+    const int gwarp = blockIdx.x * (kThreadsB / 32) + (tid >> 5);
+    const int nitems = a.B * sa.cpi;
+    const int SR = sa.nstrip * H;                      // strip-rows per image  (< 2^31: nstrip * H <= H * W / 4)
+    unsigned long long t_start = 0;
+    int items_done = 0;
+    if (sa.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+    for (int item = gwarp; item < nitems; item += nwarps) {
+        ++items_done;
+        const int b = item / sa.cpi, wi = item - b * sa.cpi;
+        int cur = (int)((long long)SR * wi / sa.cpi);
+        const int end = (int)((long long)SR * (wi + 1) / sa.cpi);
+        const int row = item;
         {
-            const double n = a.stats[ST_SI_N], S = a.stats[ST_SI_S], nr = a.stats[ST_RP_N];
-            if (SI && n > 0.0) {
-                c1 = (float)(2.0 / n) * a.w_si * up;
-                c2 = (float)(-2.0 * (double)a.lambda * S / (n * n)) * a.w_si * up;
-            }
-            if (RP && nr > 0.0) rpn = (float)(1.0 / nr) * a.w_rp * up;
+            float acc[BF_COUNT];
+#pragma unroll
+            for (int q = 0; q < BF_COUNT; ++q) acc[q] = 0.f;
+
+            const int img = b * plane;                               // B*H*W < 2^31 (checked on the host)
+            const float* __restrict__ predb = a.pred + img;
+            const float* __restrict__ gtb = a.gt + img;
+            const float* __restrict__ rgbb = SMOOTH ? a.rgb + (size_t)b * 3 * plane : nullptr;
+            const float* __restrict__ c1b = sa.c1 + (size_t)b * (H >> 1) * W1;
+            float* __restrict__ gradb = a.grad ? a.grad + img : nullptr;
+            float abw = 0.f;
             if (SMOOTH) abw = (1.0f / ((float)(a.img_psum[b] / ((double)H * W)) + a.eps_smooth)) * a.w_smooth * up;   // a_b (:192-193)
-        }
-        float fxe = 1.f, fye = 1.f, rfx = 1.f, rfy = 1.f, cxv = 0.f, cyv = 0.f;
-        bool mk_ok = true;
-        if constexpr (RP) {
-            float fx, fy;
-            load_K(a, b, fx, fy, cxv, cyv);
-            fxe = fx + a.eps_rp;
-            fye = fy + a.eps_rp;
-            rfx = __frcp_rn(fxe);
-            rfy = __frcp_rn(fye);
-            mk_ok = markstein_safe(fxe) && markstein_safe(fye);
-        }
-        const float inx0 = a.inv_nx[0] * 0.25f * a.w_grad * up, iny0 = a.inv_ny[0] * 0.25f * a.w_grad * up;
-        const float snx = a.sm_nx * abw, sny = a.sm_ny * abw;
-        const float eps_g = a.eps_grad, eps_r = a.eps_rp;
-        constexpr float kExpScale = -1.4426950408889634f / 3.0f;    // exp(-mean_c|dI|) = 2^(kExpScale * sum_c|dI|)
+            const float snx = a.sm_nx * abw, sny = a.sm_ny * abw;
+            float fxe = 1.f, fye = 1.f, rfx = 1.f, rfy = 1.f, cxv = 0.f, cyv = 0.f;
+            bool mk_ok = true;
+            if constexpr (RP) {
+                float fx, fy;
+                load_K(a, b, fx, fy, cxv, cyv);
+                fxe = fx + a.eps_rp;
+                fye = fy + a.eps_rp;
+                rfx = __frcp_rn(fxe);
+                rfy = __frcp_rn(fye);
+                mk_ok = markstein_safe(fxe) && markstein_safe(fye);
+            }
 
-        // this warp's share of the image's strip-rows (strip-major): [cur, end)
-        const long long SR = (long long)sa.nstrip * H;
-        int cur = (int)(SR * wi / sa.wpi);
-        const int end = (int)(SR * (wi + 1) / sa.wpi);
-
-        while (cur < end) {
+            while (cur < end) {
             const int strip = cur / H, ys = cur - strip * H;
             const int ye = (end - cur < H - ys) ? ys + (end - cur) : H;     // rows [ys, ye) of this strip
             cur += ye - ys;
@@ -409,6 +467,7 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_stream_kernel(const Phas
                 // 1. issue next row's loads; they are consumed at step 4, after ~2/3 of this row's arithmetic
                 const int rn = (gy + 1 < H ? gy + 1 : gy) * W;
                 fetch(rn + gxc, rn + hx, N);
+                if (gy + kStreamPrefetchRows <= ye && gy + kStreamPrefetchRows < H) prefetch_row(b, strip, gy + kStreamPrefetchRows);
                 uchar4 mk4 = make_uchar4(0, 0, 0, 0);
                 if constexpr (HAS_MASK) mk4 = __ldg(reinterpret_cast<const uchar4*>(a.mask + img + gy * W + gxc));
                 const float2 ccv = __ldg(reinterpret_cast<const float2*>(c1b + (gy >> 1) * W1 + (gxc >> 1)));
@@ -537,15 +596,41 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_stream_kernel(const Phas
                 if (gy + 1 >= ye) break;
                 step(gy + 1, RB, RA, u1s, u1t, u0s, u0t);
             }
-        }
+            }   // segments
 
-        // this warp's partial row
+            // this share's partial row (fixed content whichever warp ran it: deterministic)
+            float v[BF_COUNT];
 #pragma unroll
-        for (int q = 0; q < BF_COUNT; ++q) {
-            const float v = warp_sum(acc[q]);
-            if (lane == q) a.b_part[(size_t)gw * BF_COUNT + q] = (double)v;
+            for (int q = 0; q < BF_COUNT; ++q) v[q] = 0.f;
+            v[BF_GX0] = warp_sum(acc[BF_GX0]);
+            v[BF_GY0] = warp_sum(acc[BF_GY0]);
+            if constexpr (SMOOTH) { v[BF_SMX] = warp_sum(acc[BF_SMX]); v[BF_SMY] = warp_sum(acc[BF_SMY]); }
+            if constexpr (RP) v[BF_RP_E] = warp_sum(acc[BF_RP_E]);
+            float mine = 0.f;
+#pragma unroll
+            for (int q = 0; q < BF_COUNT; ++q) mine = (lane == q) ? v[q] : mine;
+            if (lane < BF_COUNT) sa.chunk_part[(size_t)row * BF_COUNT + lane] = (double)mine;
+            // The warp that completes an image folds that image's rows into ONE row, in a fixed order, while the
+            // other warps keep streaming: the kernel-final reduction then reads B rows instead of thousands.
+            __threadfence();
+            int last = 0;
+            if (lane == 0) last = atomicAdd(&sa.img_cnt[b], 1u) == (unsigned)sa.cpi - 1u;
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) fold_image_rows(sa.chunk_part + (size_t)b * sa.cpi * BF_COUNT, sa.cpi, a.b_part + (size_t)b * BF_COUNT,
+                                      sa.img_cnt + b, lane);
         }
     }
+    if (sa.trace && lane == 0 && gwarp < sa.trace_cap) {
+        unsigned long long t_end;
+        unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        sa.trace[4 * gwarp + 0] = smid;
+        sa.trace[4 * gwarp + 1] = t_start;
+        sa.trace[4 * gwarp + 2] = t_end;
+        sa.trace[4 * gwarp + 3] = (unsigned long long)items_done;
+    }
+    if (!sa.finalize_inline) return;
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -556,7 +641,46 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_stream_kernel(const Phas
     if (s_last) {
         __threadfence();
         finalize_results(a, s_d);
-        if (tid == 0 && a.metrics) write_metric_results(a.stats, a.metrics, *a.results);
+        if (a.metrics) write_metric_results(a.stats, a.metrics, *a.results, tid);
+    }
+}
+
+// The pass after the streaming kernel when the smoothness term is on: grad[b, :] -= off[b] (every CTA of image b
+// derives off[b] itself from the image's folded partial row -- the same arithmetic as finalize_results), while ONE
+// extra CTA does the kernel-final reduction and writes cadl_results.  That reduction is a chain of dependent L2
+// round trips (~13 us as the streaming kernel's last CTA, with 147 SMs idle); here it runs beside the offset pass.
+__global__ void __launch_bounds__(256) stream_finish_kernel(const PhaseBArgs a, int vec_ok) {
+    __shared__ double s_d[8];
+    __shared__ float s_off;
+    // grid (bx, B + 1): row 0 is dispatched first and holds the reduction CTA, rows 1..B are the images
+    const int tid = threadIdx.x, b = (int)blockIdx.y - 1;
+    if (b < 0) {
+        if (blockIdx.x == 0) {
+            finalize_results(a, s_d);
+            if (a.metrics) write_metric_results(a.stats, a.metrics, *a.results, tid);
+        }
+        return;
+    }
+    if (tid == 0) {
+        double Lb;
+        float off;
+        smooth_image_share(a, b, __ldcg(a.b_part + (size_t)b * BF_COUNT + BF_SMX), __ldcg(a.b_part + (size_t)b * BF_COUNT + BF_SMY), Lb, off);
+        s_off = off;
+    }
+    __syncthreads();
+    const float o = s_off;
+    const int HW = a.H * a.W;
+    float* g = a.grad + (size_t)b * HW;
+    if (vec_ok) {
+        float4* g4 = reinterpret_cast<float4*>(g);
+        const int n4 = HW >> 2;
+        for (int i = blockIdx.x * blockDim.x + tid; i < n4; i += gridDim.x * blockDim.x) {
+            float4 v = g4[i];
+            v.x -= o; v.y -= o; v.z -= o; v.w -= o;
+            g4[i] = v;
+        }
+    } else {
+        for (int i = blockIdx.x * blockDim.x + tid; i < HW; i += gridDim.x * blockDim.x) g[i] -= o;
     }
 }
 

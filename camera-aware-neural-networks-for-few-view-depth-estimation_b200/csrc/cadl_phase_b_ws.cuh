@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) phase_b_ws_kernel(const PhaseBA
     if (s_last) {
         __threadfence();
         finalize_results(a, s_d);
-        if (tid == 0 && a.metrics) write_metric_results(a.stats, a.metrics, *a.results);
+        if (a.metrics) write_metric_results(a.stats, a.metrics, *a.results, tid);
     }
 }
 

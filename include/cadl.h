@@ -99,6 +99,15 @@ const char* cadl_error_string(int code);
  * persistent tile kernel (cadl_phase_b_ws.cuh).  All variants must produce the same values.  Process-global;
  * not for production use. */
 void cadl_debug_force_generic(int on);
+/* Debug trace of the streaming phase-B kernel: while dev_buf is non-NULL every warp (global index < capacity_warps)
+ * writes {SM id, start globaltimer ns, end globaltimer ns, work items processed} as 4 x uint64 at dev_buf[4*warp].
+ * NULL switches it off.  Process-global; profiling aid (profiles/trace_stream.py), not for production use. */
+void cadl_debug_set_trace(unsigned long long* dev_buf, int capacity_warps);
+/* Debug timing: with enable != 0 every following cadl_stack_fwd_bwd call records a CUDA event after each of its
+ * launches and SYNCHRONISES at the end.  Returns the number of intervals of the LAST timed call and copies up to
+ * cap of them: ms_out[i] = milliseconds up to the end of the launch names_out[i] (static strings; the last
+ * interval, "end", is whatever follows the last named kernel).  Process-global; profiling aid only. */
+int cadl_debug_kernel_times(int enable, float* ms_out, const char** names_out, int cap);
 /* Test hook: counts (into *mismatches_dev, a device uint64 the caller zeroed) the inputs with bit pattern in
  * [lo_bits, hi_bits] for which a device-math replica differs from the CUDA library form.
  *   which 0: log replica (scalar and packed fp32x2) vs logf;  which 1: Markstein a/param vs IEEE division. */

@@ -85,6 +85,7 @@ struct Ws {
 
 int g_force_generic = 0;
 int g_force_tile = 0;
+int g_no_pdl = 0;           // bit 4: plain stream-ordered launches (no programmatic dependent launch)
 // cadl_debug_kernel_times: CUDA events between the launches of one cadl_stack_fwd_bwd call (debug / profiling aid)
 struct KTimes {
     bool on = false;
@@ -255,19 +256,36 @@ cudaError_t launch_fast(PhaseBArgs& a, cudaStream_t st) {
     return a.mask ? launch_fast_m<F, true>(a, st) : launch_fast_m<F, false>(a, st);
 }
 
+// Launch with programmatic stream serialization: the kernel may start while its predecessor in the stream drains;
+// it calls pdl_wait() (cadl_math.cuh) before it touches anything the predecessor wrote.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // streaming split of the fast path: pooled pyramid -> coarse coefficients -> full-resolution pass (cadl_phase_b_stream.cuh)
 template <int F>
 cudaError_t launch_stream(PhaseBArgs& a, const Ws& ws, cudaStream_t st, bool* offset_done) {
     const PyrArrays py = ws.pyr();
     const int nblk = ws.L.pyr_blocks;
-    pyr_pool_kernel<<<nblk, 256, 0, st>>>(a.pred, a.gt, a.B, a.H, a.W, a.eps_grad, py, ws.img_cnt());
+    const bool pdl = !g_no_pdl && !g_kt.on;          // (event records between the launches would serialise them anyway)
+    cudaError_t e = launch_pdl(pyr_pool_kernel, dim3(nblk), dim3(256), st, pdl, a.pred, a.gt, a.B, a.H, a.W, a.eps_grad, py,
+                               ws.img_cnt());
+    if (e != cudaSuccess) return e;
     kt_mark(st, "pyr_pool_kernel");
     PyrCoefArgs ca{};
     ca.py = py; ca.B = a.B; ca.H = a.H; ca.W = a.W;
     for (int s = 0; s < 4; ++s) { ca.inv_nx[s] = a.inv_nx[s]; ca.inv_ny[s] = a.inv_ny[s]; }
     ca.wg = 0.25f * a.w_grad * a.upstream;          // 1/num_scales * weight * upstream
     ca.b_part = a.b_part; ca.row0 = a.B;             // final rows: [B per-image rows][nblk rows of this kernel]
-    pyr_coef_kernel<<<nblk, 256, 0, st>>>(ca);
+    e = launch_pdl(pyr_coef_kernel, dim3(nblk), dim3(256), st, pdl, ca);
+    if (e != cudaSuccess) return e;
     kt_mark(st, "pyr_coef_kernel");
     StreamArgs sa{};
     sa.c1 = py.c1; sa.nstrip = (a.W + 127) / 128;
@@ -291,8 +309,9 @@ cudaError_t launch_stream(PhaseBArgs& a, const Ws& ws, cudaStream_t st, bool* of
     sa.finalize_inline = defer ? 0 : 1;
     int grid = (a.B * sa.cpi + kThreadsB / 32 - 1) / (kThreadsB / 32);
     if (grid > 2 * num_sms) grid = 2 * num_sms;
-    if (a.mask) phase_b_stream_kernel<F, true><<<grid, kThreadsB, 0, st>>>(a, sa);
-    else phase_b_stream_kernel<F, false><<<grid, kThreadsB, 0, st>>>(a, sa);
+    if (a.mask) e = launch_pdl(phase_b_stream_kernel<F, true>, dim3(grid), dim3(kThreadsB), st, pdl, a, sa);
+    else e = launch_pdl(phase_b_stream_kernel<F, false>, dim3(grid), dim3(kThreadsB), st, pdl, a, sa);
+    if (e != cudaSuccess) return e;
     kt_mark(st, "phase_b_stream_kernel");
     if (defer) {
         const int HW = a.H * a.W;
@@ -301,7 +320,8 @@ cudaError_t launch_stream(PhaseBArgs& a, const Ws& ws, cudaStream_t st, bool* of
         int cap = (148 * 8 + a.B - 1) / a.B;
         if (bx > cap) bx = cap;
         if (bx < 1) bx = 1;
-        stream_finish_kernel<<<dim3(bx, a.B + 1), 256, 0, st>>>(a, vec);
+        e = launch_pdl(stream_finish_kernel, dim3(bx, a.B + 1), dim3(256), st, pdl, a, vec);
+        if (e != cudaSuccess) return e;
         kt_mark(st, "stream_finish_kernel");
         *offset_done = true;
     }
@@ -500,6 +520,7 @@ void cadl_debug_force_generic(int on) {
     g_force_generic = on & 1;
     g_force_no_tma = (on >> 1) & 1;
     g_force_tile = (on >> 3) & 1;
+    g_no_pdl = (on >> 4) & 1;
     g_use_ws = (on >> 2) & 1;
 }
 size_t cadl_sizeof_params(void) { return sizeof(cadl_params); }

@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(kThreadsA, 4) phase_a_kernel(const PhaseAArgs 
     __shared__ float s_to[kToSlots * kThreadsA];
     __shared__ unsigned s_iw[kThreadsA / 32][AI_COUNT];
 
+    pdl_trigger();   // the pooled-pyramid kernel that follows reads only pred/gt: let it fill SMs as this grid drains
     const int b = blockIdx.y, k = blockIdx.x;
     const int tid = threadIdx.x;
     constexpr bool has_mask = HAS_MASK;

@@ -45,13 +45,17 @@ struct PyrArrays {
 __global__ void __launch_bounds__(256) pyr_pool_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
                                                        int B, int H, int W, float eps, PyrArrays py,
                                                        unsigned int* img_cnt) {
+    // Launched with programmatic stream serialization behind phase A, of which it needs nothing: it starts as
+    // phase A's CTAs drain.  It only has to END after phase A (pdl_wait below), so that the kernels behind it,
+    // which wait for THIS grid, also see phase A's statistics.
+    pdl_trigger();
     const int W8 = W >> 3, H8 = H >> 3;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     // the streaming kernel's per-image completion counters (stream-ordered before it; their offset depends on the
     // shape, and one workspace serves calls of different shapes)
     if (blockIdx.x == 0)
         for (int i = threadIdx.x; i < B; i += blockDim.x) img_cnt[i] = 0u;
-    if (idx >= B * H8 * W8) return;
+    if (idx >= B * H8 * W8) { pdl_wait(); return; }
     const int bx = idx % W8, by = (idx / W8) % H8, b = idx / (W8 * H8);
     const float* pp = pred + (size_t)b * H * W + (size_t)(by * 8) * W + bx * 8;
     const float* gp = gt + (size_t)b * H * W + (size_t)(by * 8) * W + bx * 8;
@@ -113,6 +117,7 @@ __global__ void __launch_bounds__(256) pyr_pool_kernel(const float* __restrict__
         py.lg[2][o] = l.y;
         py.rq[2][o] = in_range_pos(q, eps, 1000.0f) ? rcp_approx(q) : 0.f;
     }
+    pdl_wait();
 }
 
 // ================================================================================================
@@ -199,6 +204,8 @@ struct PyrCoefArgs {
 
 __global__ void __launch_bounds__(256) pyr_coef_kernel(const PyrCoefArgs a) {
     __shared__ float s_f[8][6];
+    pdl_wait();        // the pooled arrays of pyr_pool_kernel
+    pdl_trigger();
     const int W8 = a.W >> 3, H8 = a.H >> 3;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // GX1, GY1, GX2, GY2, GX3, GY3
@@ -310,6 +317,8 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_stream_kernel(const Phas
     const float eps_g = a.eps_grad, eps_r = a.eps_rp;
     constexpr float kExpScale = -1.4426950408889634f / 3.0f;    // exp(-mean_c|dI|) = 2^(kExpScale * sum_c|dI|)
 
+    pdl_trigger();
+    pdl_wait();        // C1 of pyr_coef_kernel, and through it the statistics of phase A
     // scalars derived from the phase-A statistics, weights and upstream folded in
     float c1 = 0.f, c2 = 0.f, rpn = 0.f;
     {
@@ -654,6 +663,7 @@ __global__ void __launch_bounds__(256) stream_finish_kernel(const PhaseBArgs a, 
     __shared__ float s_off;
     // grid (bx, B + 1): row 0 is dispatched first and holds the reduction CTA, rows 1..B are the images
     const int tid = threadIdx.x, b = (int)blockIdx.y - 1;
+    pdl_wait();        // the gradient and the partial rows of phase_b_stream_kernel
     if (b < 0) {
         if (blockIdx.x == 0) {
             finalize_results(a, s_d);

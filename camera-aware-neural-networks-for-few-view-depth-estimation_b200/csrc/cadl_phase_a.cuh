@@ -33,8 +33,12 @@ struct PhaseAArgs {
 // ~1e-5 per pixel) are the two IEEE divisions of depth_metrics.h:221 / trainer :433 actually performed.
 __device__ __forceinline__ float ratio_for_thresholds(float p, float g, float rp, float rg) {
     float ratio = fmaxf(p * rg, g * rp);
-    const bool near = (fabsf(ratio - 1.25f) < 4e-6f) || (fabsf(ratio - 1.5625f) < 5e-6f) ||
-                      (fabsf(ratio - 1.953125f) < 6e-6f) || !(ratio == ratio);
+    // guard bands of 34 / 42 / 51 ulps (4e-6, 5e-6, 6e-6) around 1.25, 1.5625, 1.953125, tested on the bit
+    // patterns: one integer subtract + one unsigned compare each.  (A NaN or infinite ratio is outside every band
+    // and compares false against the thresholds exactly like the IEEE quotients would.)
+    const int u = __float_as_int(ratio);
+    const bool near = ((unsigned)(u - (0x3FA00000 - 34)) <= 68u) || ((unsigned)(u - (0x3FC80000 - 42)) <= 84u) ||
+                      ((unsigned)(u - (0x3FFA0000 - 51)) <= 102u);
     if (near) ratio = fmaxf(__fdiv_rn(p, g), __fdiv_rn(g, p));
     return ratio;
 }
@@ -302,6 +306,7 @@ __global__ void __launch_bounds__(kThreadsA, 4) phase_a_kernel(const PhaseAArgs 
     // fixed shuffle tree, fixed warp order: deterministic.  __ldcg: rows written by other SMs (fence + ticket).
     __shared__ double s_wa[kThreadsA / 32][AF_COUNT];
     constexpr int kHalf = (AF_COUNT + 1) / 2;
+    if constexpr ((F & ~FA_RP) != 0)          // the reprojection count alone has no float partial rows
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         double accq[kHalf];

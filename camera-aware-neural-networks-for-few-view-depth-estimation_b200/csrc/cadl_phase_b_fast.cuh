@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
 // Requires W % 4 == 0 and 16-byte aligned tensors (same dispatch condition as the tile fast path).
 // ================================================================================================
 template <int F, bool HAS_MASK>
-__global__ void __launch_bounds__(kThreadsB) phase_b_point_fast_kernel(const PhaseBArgs a) {
+__global__ void __launch_bounds__(kThreadsB, 4) phase_b_point_fast_kernel(const PhaseBArgs a) {
     __shared__ float s_f[kThreadsB / 32][BF_COUNT];
     __shared__ double s_d[8];
     __shared__ float s_c[4];

@@ -12,8 +12,9 @@ B=32 images of 480x640 per GPU (BASELINE config 3).  Prints ONE JSON line (rank 
   e2e       the same metric through the reference-facing C++ API (drop-in CombinedDepthLoss +
             DepthMetrics via host/libcadl_host.so) with pinned HOST buffers: H2D of pred/gt/rgb/K and the
             D2H of the loss scalar + metric blocks are inside the timed region
-  roofline  for the dominant kernel (phase_b_fast_kernel): algorithmic bytes (24 B/px: read pred, gt,
-            3 x rgb, write grad) / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  roofline  for the dominant kernel (phase_b_stream_kernel): algorithmic bytes (24 B/px: read pred, gt,
+            3 x rgb, write grad) / its CUDA-event duration (events recorded on the launching stream around each
+            launch of the step: cadl_debug_kernel_times), against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the unmodified reference headers on LibTorch CPU (oracle/_ref) timed on this box
 
 --impl reference times the reference's own CPU implementation (same harness source compiled against the
@@ -234,6 +235,16 @@ def main():
         # per-phase durations for the roofline of the dominant kernel (same launches, timed apart)
         ms_a = timed(lambda: pkg.stack_reduce(pred, gt, None, params, ws), args.steps, 3)
         ms_b = timed(lambda: pkg.stack_grad(pred, gt, rgb, K, None, params, grad, ws), args.steps, 3)
+        # every launch of the step between its own pair of CUDA events (this mode synchronises after each step and
+        # switches the programmatic dependent launches off, so the intervals include the launch gaps)
+        per_launch = {}
+        pkg.kernel_times(True)
+        for _ in range(30):
+            step()
+            for name, ms in pkg.kernel_times(True):
+                per_launch.setdefault(name, []).append(ms)
+        pkg.kernel_times(False)
+        per_launch = {k: statistics.median(v) for k, v in per_launch.items()}
         # config 2 (reprojection alone) as a secondary figure
         p2 = pkg.default_params(terms=pkg.TERM_REPROJ, w_reproj=1.0)
         ms_rp = timed(lambda: pkg.stack_fwd_bwd(pred, gt, None, K, None, params=p2, grad=grad, ws=ws), args.steps, 3)
@@ -248,17 +259,19 @@ def main():
     value = world * P / (ms_step * 1e-3) / 1e6
 
     peak, peak_src = hbm_peak()
-    achieved = ALGO_BYTES_PER_PX * P / (ms_b * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "phase_b_fast_kernel<15,false> (+ smooth_offset_kernel)",
+    ms_k = per_launch.get("phase_b_stream_kernel", ms_b)
+    achieved = ALGO_BYTES_PER_PX * P / (ms_k * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "phase_b_stream_kernel<15,false>",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX * P,
-                "kernel_ms": ms_b, "phase_a_ms": ms_a,
+                "kernel_ms": ms_k, "phase_a_ms": ms_a, "phase_b_ms": ms_b,
+                "per_launch_ms": per_launch,
                 "step_frac": ALGO_BYTES_PER_PX * P / (ms_step * 1e-3) / 1e9 / peak}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get("phase_b_tile_kernel_bytes_per_launch")
+            roofline["traffic"] = json.load(open(traffic_file)).get("phase_b_stream_kernel_bytes_per_launch")
         except Exception:
             pass
     reproj = {"workload": "config2: reprojection alone fwd+bwd, B=32 480x640", "ms_per_step": ms_rp,
@@ -322,8 +335,9 @@ def main():
                        "l2": "inputs+gradient 275 MB per step > 126 MB L2 (no flush needed)",
                        "seed": "1234 + rank"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": 3 * args.steps, "launches_per_step": ["phase_a_kernel<31,false>", "phase_b_fast_kernel<15,false>",
-                                                                   "smooth_offset_kernel"],
+            "gpu_launches": 5 * args.steps,
+            "launches_per_step": ["phase_a_kernel<31,false>", "pyr_pool_kernel", "pyr_coef_kernel",
+                                  "phase_b_stream_kernel<15,false>", "stream_finish_kernel"],
             "clocks": clocks, "also": reproj,
         }
         print(json.dumps(line), flush=True)

@@ -330,18 +330,11 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_stream_kernel(const Phas
         if (RP && nr > 0.0) rpn = (float)(1.0 / nr) * a.w_rp * up;
     }
 
-    // lanes 0..19 each own one 128-byte line of a 128-column row segment: pred, gt, 3 x rgb  x 4 lines
+    // L2 prefetch kStreamPrefetchRows rows ahead of the register loads: lanes 0..19 each own one 128-byte line of a
+    // 128-column row segment (pred, gt, 3 x rgb  x 4 lines); the pointer is set up per segment and advanced by a row
     const int pf_t = lane >> 2, pf_seg = lane & 3;
-    auto prefetch_row = [&](int b, int strip, int y) {
-        const int x = strip * 128 + pf_seg * 32;
-        if (lane < (SMOOTH ? 20 : 8) && x < W) {
-            const float* base = pf_t == 0 ? a.pred + (size_t)b * plane
-                              : pf_t == 1 ? a.gt + (size_t)b * plane
-                                          : a.rgb + ((size_t)b * 3 + (pf_t - 2)) * plane;
-            prefetch_l2(base + (size_t)y * W + x);
-        }
-    };
-
+    const bool pf_lane = lane < (SMOOTH ? 20 : 8);
+    const size_t rowbytes = (size_t)W * sizeof(float);
     // Work items: every image's strip-rows (strip-major) cut into cpi equal shares, one per warp of the single
     // resident wave (more than one per warp only for huge batches).  cadl_debug_set_trace shows warps finishing
     // within +-12 % of each other; handing the last quarter of each image out dynamically in 4-row chunks was
@@ -364,12 +357,11 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_stream_kernel(const Phas
 #pragma unroll
             for (int q = 0; q < BF_COUNT; ++q) acc[q] = 0.f;
 
-            const int img = b * plane;                               // B*H*W < 2^31 (checked on the host)
-            const float* __restrict__ predb = a.pred + img;
-            const float* __restrict__ gtb = a.gt + img;
+            // pred / gt / grad / C1 are addressed as (kernel-parameter base) + 32-bit element offset, so no per-image
+            // 64-bit pointers stay live across the row loop (B*H*W < 2^31, checked on the host); rgb needs 64 bits
+            const int img = b * plane;
+            const int c1img = b * (H >> 1) * W1;
             const float* __restrict__ rgbb = SMOOTH ? a.rgb + (size_t)b * 3 * plane : nullptr;
-            const float* __restrict__ c1b = sa.c1 + (size_t)b * (H >> 1) * W1;
-            float* __restrict__ gradb = a.grad ? a.grad + img : nullptr;
             float abw = 0.f;
             if (SMOOTH) abw = (1.0f / ((float)(a.img_psum[b] / ((double)H * W)) + a.eps_smooth)) * a.w_smooth * up;   // a_b (:192-193)
             const float snx = a.sm_nx * abw, sny = a.sm_ny * abw;
@@ -400,24 +392,22 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_stream_kernel(const Phas
             // border, so that edge vanishes), left neighbour for lane 0 (itself at the left border)
             const int hx = lastlane ? (gx0 + 4 < W ? gx0 + 4 : W - 1) : (gx0 >= 1 ? gx0 - 1 : 0);
             const bool left_edge = (lane == 0) && (gx0 >= 1);    // lane 0 evaluates the edge to its left neighbour strip
-            float axk[4] = {0.f, 0.f, 0.f, 0.f}, xhk[4] = {0.f, 0.f, 0.f, 0.f};
-            if constexpr (RP) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    axk[k] = (float)(gx0 + k) - cxv;
-                    xhk[k] = axk[k] * rfx;                       // d pX / d p: tolerance path
-                }
-            }
+            const bool pf_on = pf_lane && (strip * 128 + pf_seg * 32 < W);
+            const int pf_end = ye + 1 < H ? ye + 1 : H;              // rows [.., ye] are read by this segment
+            const char* pf_ptr = reinterpret_cast<const char*>(
+                (pf_t == 0 ? a.pred + img : pf_t == 1 ? a.gt + img : a.rgb + ((size_t)b * 3 + (pf_t >= 2 ? pf_t - 2 : 0)) * plane) +
+                (size_t)(ys + kStreamPrefetchRows) * W + strip * 128 + pf_seg * 32);
+            const float ufx0 = (float)gx0;                       // u of the lane's first pixel; u + k is exact
 
             // issue the global loads of one image row; rows outside the image are the border row again (every
             // vertical edge across the border then has residual exactly 0).  No use of the values here.
             auto fetch = [&](int off, int offh, StreamRow& R) {
-                const float4 p4 = __ldg(reinterpret_cast<const float4*>(predb + off));
-                const float4 g4 = __ldg(reinterpret_cast<const float4*>(gtb + off));
+                const float4 p4 = __ldg(reinterpret_cast<const float4*>(a.pred + (img + off)));
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.gt + (img + off)));
                 R.p[0] = p4.x; R.p[1] = p4.y; R.p[2] = p4.z; R.p[3] = p4.w;
                 R.g[0] = g4.x; R.g[1] = g4.y; R.g[2] = g4.z; R.g[3] = g4.w;
-                R.hp = __ldg(predb + offh);
-                R.hg = __ldg(gtb + offh);
+                R.hp = __ldg(a.pred + (img + offh));
+                R.hg = __ldg(a.gt + (img + offh));
                 if constexpr (SMOOTH) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
@@ -476,10 +466,11 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_stream_kernel(const Phas
                 // 1. issue next row's loads; they are consumed at step 4, after ~2/3 of this row's arithmetic
                 const int rn = (gy + 1 < H ? gy + 1 : gy) * W;
                 fetch(rn + gxc, rn + hx, N);
-                if (gy + kStreamPrefetchRows <= ye && gy + kStreamPrefetchRows < H) prefetch_row(b, strip, gy + kStreamPrefetchRows);
+                if (pf_on && gy + kStreamPrefetchRows < pf_end) prefetch_l2(pf_ptr);
+                pf_ptr += rowbytes;
                 uchar4 mk4 = make_uchar4(0, 0, 0, 0);
                 if constexpr (HAS_MASK) mk4 = __ldg(reinterpret_cast<const uchar4*>(a.mask + img + gy * W + gxc));
-                const float2 ccv = __ldg(reinterpret_cast<const float2*>(c1b + (gy >> 1) * W1 + (gxc >> 1)));
+                const float2 ccv = __ldg(reinterpret_cast<const float2*>(sa.c1 + (c1img + (gy >> 1) * W1 + (gxc >> 1))));
 
                 // 2. horizontal edges of the current row: each lane evaluates the four edges to the right of its
                 //    pixels; the sign of the edge to its left comes from the left lane
@@ -548,15 +539,17 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_stream_kernel(const Phas
                         const bool m = HAS_MASK ? um[k] : (g > eps_r);
                         if (m && lane_in) {
                             // same operations, same order as depth_loss.h:299-315 (see cadl_phase_b.cuh)
+                            const float axk = __fadd_rn(__fadd_rn(ufx0, (float)k), -cxv);      // (u - cx), u = float(column)
+                            const float xhk = axk * rfx;                                       // d pX / d p: tolerance path
                             float pX, gX, pY, gY;
                             if (mk_ok) {
-                                pX = div_by_const(__fmul_rn(axk[k], p), fxe, rfx);
-                                gX = div_by_const(__fmul_rn(axk[k], g), fxe, rfx);
+                                pX = div_by_const(__fmul_rn(axk, p), fxe, rfx);
+                                gX = div_by_const(__fmul_rn(axk, g), fxe, rfx);
                                 pY = div_by_const(__fmul_rn(ayv, p), fye, rfy);
                                 gY = div_by_const(__fmul_rn(ayv, g), fye, rfy);
                             } else {
-                                pX = __fdiv_rn(__fmul_rn(axk[k], p), fxe);
-                                gX = __fdiv_rn(__fmul_rn(axk[k], g), fxe);
+                                pX = __fdiv_rn(__fmul_rn(axk, p), fxe);
+                                gX = __fdiv_rn(__fmul_rn(axk, g), fxe);
                                 pY = __fdiv_rn(__fmul_rn(ayv, p), fye);
                                 gY = __fdiv_rn(__fmul_rn(ayv, g), fye);
                             }
@@ -564,7 +557,7 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_stream_kernel(const Phas
                             const float ss = fmaf(dZ, dZ, fmaf(dY, dY, dX * dX)) + eps_r;
                             const float re = rsqrt_approx(ss);
                             acc[BF_RP_E] = fmaf(ss, re, acc[BF_RP_E]);              // e = sqrt(ss)
-                            gsum = fmaf(fmaf(dX, xhk[k], fmaf(dY, yh, dZ)) * re, rpn, gsum);
+                            gsum = fmaf(fmaf(dX, xhk, fmaf(dY, yh, dZ)) * re, rpn, gsum);
                         }
                     }
                     pw[k] = gsum;
@@ -584,8 +577,8 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_stream_kernel(const Phas
                     gsum = in_range_pos(C.p[k], eps_g, 1000.0f) ? fmaf(gmk, rpk[k], gsum) : gsum;   // clamp backward
                     out[k] = gsum;
                 }
-                if (gradb && lane_in)
-                    *reinterpret_cast<float4*>(gradb + gy * W + gx0) = make_float4(out[0], out[1], out[2], out[3]);
+                if (a.grad && lane_in)
+                    *reinterpret_cast<float4*>(a.grad + (img + gy * W + gx0)) = make_float4(out[0], out[1], out[2], out[3]);
             };
 
             // prologue: the row above this segment only contributes its lower edges

@@ -65,3 +65,51 @@ def test_fast_kernel_equals_generic_kernel(pkg, shape, terms):
     scale = float(gg.abs().max())
     assert float((gf - gg).abs().max()) <= 2e-6 * scale
     assert torch.equal(gf, gc)
+
+
+@pytest.mark.parametrize("shape,masked", [((2400, 8, 8), False),     # more images than resident warps: several shares per warp
+                                          ((1, 16, 16), False),      # fewer strip-rows than warps
+                                          ((3, 40, 200), True),      # partial last strip (200 = 128 + 72), explicit mask
+                                          ((2, 64, 136), False),     # 8 columns in the last strip
+                                          ((5, 24, 384), True)])
+def test_streaming_path_work_partition(pkg, shape, masked):
+    """The streaming fast path against the generic kernel on shapes that stress its work partition: shares that span
+    strips, warps with no or several shares, partial strips, masks; with and without the dispatch-mode overrides
+    (16 = no programmatic dependent launch)."""
+    B, H, W = shape
+    d = torch.device("cuda:0")
+    b = pkg.synth.make_batch(B, H, W, seed=B + H + W, device=d)
+    mask = (torch.rand(B, 1, H, W, device=d) < 0.8) if masked else None
+    res = {}
+    for mode in (1, 0, 16):
+        pkg.force_generic(mode)
+        try:
+            ws = pkg.stack_fwd_bwd(b["pred"], b["gt"], b["rgb"], b["K"], mask, params=pkg.default_params(metrics=3))
+            torch.cuda.synchronize()
+            res[mode] = (pkg.results_dict(ws.read_results()), ws.grad.clone())
+        finally:
+            pkg.force_generic(0)
+    (rg, gg), (rs, gs), (rn, gn) = res[1], res[0], res[16]
+    assert torch.equal(gs, gn)
+    for k in ("loss_total", "si_loss", "grad_loss", "smooth_loss", "reproj_loss"):
+        assert rel_err(rs[k], rg[k]) <= 2e-6, (k, rs[k], rg[k])
+        assert rel_err(rs[k], rn[k]) == 0.0          # NaN-aware (8x8: the coarsest scale has no x-edges, mean of nothing)
+    assert float((gs - gg).abs().max()) <= 2e-6 * float(gg.abs().max())
+    assert rs["eval_counts"] == rg["eval_counts"] and rs["train_counts"] == rg["train_counts"]
+
+
+def test_streaming_path_forward_only_and_repeatable(pkg):
+    """grad = None (forward only: the streaming kernel's last CTA writes the results itself) gives the same losses,
+    and two runs of the full step are bit-identical (fixed reduction order, no floating-point atomics)."""
+    d = torch.device("cuda:0")
+    b = pkg.synth.make_batch(4, 96, 256, seed=77, device=d)
+    p = pkg.default_params(metrics=3)
+    w1 = pkg.stack_fwd_bwd(b["pred"], b["gt"], b["rgb"], b["K"], None, params=p)
+    r1, g1 = pkg.results_dict(w1.read_results()), w1.grad.clone()
+    w2 = pkg.stack_fwd_bwd(b["pred"], b["gt"], b["rgb"], b["K"], None, params=p)
+    r2, g2 = pkg.results_dict(w2.read_results()), w2.grad.clone()
+    assert torch.equal(g1, g2) and r1 == r2
+    w3 = pkg.stack_fwd_bwd(b["pred"], b["gt"], b["rgb"], b["K"], None, params=p, want_grad=False)
+    r3 = pkg.results_dict(w3.read_results())
+    for k in ("loss_total", "si_loss", "grad_loss", "smooth_loss", "reproj_loss"):
+        assert r3[k] == r1[k], (k, r3[k], r1[k])

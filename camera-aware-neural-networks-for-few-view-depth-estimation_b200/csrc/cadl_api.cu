@@ -85,6 +85,7 @@ struct Ws {
 
 int g_force_generic = 0;
 int g_force_tile = 0;
+int g_no_overlap = 0;       // bit 5: pooled-pyramid kernels in line on the caller's stream instead of beside phase A
 int g_no_pdl = 0;           // bit 4: plain stream-ordered launches (no programmatic dependent launch)
 // cadl_debug_kernel_times: CUDA events between the launches of one cadl_stack_fwd_bwd call (debug / profiling aid)
 struct KTimes {
@@ -269,13 +270,48 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStre
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-// streaming split of the fast path: pooled pyramid -> coarse coefficients -> full-resolution pass (cadl_phase_b_stream.cuh)
-template <int F>
-cudaError_t launch_stream(PhaseBArgs& a, const Ws& ws, cudaStream_t st, bool* offset_done) {
+int num_sms_cached() {
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return num_sms;
+}
+
+// How one cadl_stack_fwd_bwd call is laid out over launches (decided once, used by the reduce and the gradient part).
+struct StepPlan {
+    bool pyr_prelaunched = false;   // the pooled-pyramid kernels already run on the auxiliary stream, beside phase A
+    int pyr_grid = 0;               // CTAs (= partial rows) of pyr_coef_kernel; 0 = one thread per 8x8 block
+    int a_blocks_per_img = 0;       // phase A grid override (0 = the workspace layout's)
+};
+
+// The pooled-pyramid kernels need pred/gt only, phase A needs pred/gt only, and neither needs the other: they run
+// SIDE BY SIDE -- the pyramid as one persistent CTA per SM on an auxiliary stream (memory-latency bound, few issue
+// slots), phase A on the caller's stream with its grid shrunk so that both fit in one resident wave.
+struct AuxStream {
+    cudaStream_t s2 = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    int dev = -1;
+};
+thread_local AuxStream g_aux[16];
+AuxStream* aux_for_current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    AuxStream& x = g_aux[dev];
+    if (x.dev != dev) {
+        if (cudaStreamCreateWithFlags(&x.s2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        x.dev = dev;
+    }
+    return &x;
+}
+
+cudaError_t launch_pyramid(const PhaseBArgs& a, const Ws& ws, cudaStream_t st, int grid, bool pdl_pool, bool pdl) {
     const PyrArrays py = ws.pyr();
-    const int nblk = ws.L.pyr_blocks;
-    const bool pdl = !g_no_pdl && !g_kt.on;          // (event records between the launches would serialise them anyway)
-    cudaError_t e = launch_pdl(pyr_pool_kernel, dim3(nblk), dim3(256), st, pdl, a.pred, a.gt, a.B, a.H, a.W, a.eps_grad, py,
+    cudaError_t e = launch_pdl(pyr_pool_kernel, dim3(grid), dim3(256), st, pdl_pool, a.pred, a.gt, a.B, a.H, a.W, a.eps_grad, py,
                                ws.img_cnt());
     if (e != cudaSuccess) return e;
     kt_mark(st, "pyr_pool_kernel");
@@ -283,24 +319,35 @@ cudaError_t launch_stream(PhaseBArgs& a, const Ws& ws, cudaStream_t st, bool* of
     ca.py = py; ca.B = a.B; ca.H = a.H; ca.W = a.W;
     for (int s = 0; s < 4; ++s) { ca.inv_nx[s] = a.inv_nx[s]; ca.inv_ny[s] = a.inv_ny[s]; }
     ca.wg = 0.25f * a.w_grad * a.upstream;          // 1/num_scales * weight * upstream
-    ca.b_part = a.b_part; ca.row0 = a.B;             // final rows: [B per-image rows][nblk rows of this kernel]
-    e = launch_pdl(pyr_coef_kernel, dim3(nblk), dim3(256), st, pdl, ca);
+    ca.b_part = a.b_part; ca.row0 = a.B;             // final rows: [B per-image rows][one row per CTA of this kernel]
+    e = launch_pdl(pyr_coef_kernel, dim3(grid), dim3(256), st, pdl, ca);
     if (e != cudaSuccess) return e;
     kt_mark(st, "pyr_coef_kernel");
+    return cudaSuccess;
+}
+
+// streaming split of the fast path: pooled pyramid -> coarse coefficients -> full-resolution pass (cadl_phase_b_stream.cuh)
+template <int F>
+cudaError_t launch_stream(PhaseBArgs& a, const Ws& ws, cudaStream_t st, bool* offset_done, const StepPlan& plan) {
+    const PyrArrays py = ws.pyr();
+    const int nblk = plan.pyr_grid > 0 ? plan.pyr_grid : ws.L.pyr_blocks;
+    // (event records between the launches would serialise them anyway; after a cross-stream join the streaming
+    //  kernel has two predecessors and is launched plainly)
+    const bool pdl = !g_no_pdl && !g_kt.on;
+    cudaError_t e = cudaSuccess;
+    if (!plan.pyr_prelaunched) {
+        e = launch_pyramid(a, ws, st, nblk, pdl, pdl);
+        if (e != cudaSuccess) return e;
+    }
     StreamArgs sa{};
     sa.c1 = py.c1; sa.nstrip = (a.W + 127) / 128;
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int num_sms = num_sms_cached();
     const int wave = 2 * num_sms * (kThreadsB / 32);                 // resident warps: 2 CTAs x 8 warps per SM (128 registers)
     const int SR = sa.nstrip * a.H;
     sa.cpi = wave / a.B > 0 ? wave / a.B : 1;
     if (sa.cpi > ws.L.stream_cpi) sa.cpi = ws.L.stream_cpi;         // workspace sized for this many rows per image
     if (sa.cpi > SR) sa.cpi = SR;
-    sa.chunk_part = a.b_part + (size_t)(a.B + nblk) * BF_COUNT;
+    sa.chunk_part = a.b_part + (size_t)(a.B + ws.L.pyr_blocks) * BF_COUNT;
     sa.img_cnt = ws.img_cnt();
     a.tiles_x = 1; a.tiles_y = 1;                    // finalize_results: one (already reduced) row per image
     a.b_rows = a.B + nblk;
@@ -309,8 +356,9 @@ cudaError_t launch_stream(PhaseBArgs& a, const Ws& ws, cudaStream_t st, bool* of
     sa.finalize_inline = defer ? 0 : 1;
     int grid = (a.B * sa.cpi + kThreadsB / 32 - 1) / (kThreadsB / 32);
     if (grid > 2 * num_sms) grid = 2 * num_sms;
-    if (a.mask) e = launch_pdl(phase_b_stream_kernel<F, true>, dim3(grid), dim3(kThreadsB), st, pdl, a, sa);
-    else e = launch_pdl(phase_b_stream_kernel<F, false>, dim3(grid), dim3(kThreadsB), st, pdl, a, sa);
+    const bool pdl_s = pdl && !plan.pyr_prelaunched;
+    if (a.mask) e = launch_pdl(phase_b_stream_kernel<F, true>, dim3(grid), dim3(kThreadsB), st, pdl_s, a, sa);
+    else e = launch_pdl(phase_b_stream_kernel<F, false>, dim3(grid), dim3(kThreadsB), st, pdl_s, a, sa);
     if (e != cudaSuccess) return e;
     kt_mark(st, "phase_b_stream_kernel");
     if (defer) {
@@ -352,7 +400,7 @@ cudaError_t launch_point(const PhaseBArgs& a, cudaStream_t st) {
 }
 
 int run_reduce(const float* pred, const float* gt, const uint8_t* mask, int B, int H, int W,
-               const cadl_params& p, const Ws& ws, cudaStream_t st) {
+               const cadl_params& p, const Ws& ws, cudaStream_t st, const StepPlan& plan = StepPlan()) {
     uint32_t f = phase_a_flags(p);
     if (f == 0) return CADL_OK;
     const bool need_p = f & (FA_SI | FA_PSUM | FA_EV | FA_TR);
@@ -362,6 +410,7 @@ int run_reduce(const float* pred, const float* gt, const uint8_t* mask, int B, i
     a.pred = pred; a.gt = gt; a.mask = mask;
     a.B = B; a.HW = H * W;
     a.blocks_per_img = ws.L.a_blocks_per_img;
+    if (plan.a_blocks_per_img > 0 && plan.a_blocks_per_img < a.blocks_per_img) a.blocks_per_img = plan.a_blocks_per_img;
     a.vec_ok = ((H * W) % 4 == 0) && (!pred || aligned(pred, 16)) && (!gt || aligned(gt, 16)) &&
                (!mask || aligned(mask, 4));
     a.eps_si = p.eps_si; a.eps_rp = p.eps_reproj; a.min_d = p.min_depth; a.max_d = p.max_depth;
@@ -373,16 +422,16 @@ int run_reduce(const float* pred, const float* gt, const uint8_t* mask, int B, i
     return cuda_rc(dispatch_a(f, a, grid, st));
 }
 
-int run_grad(const float* pred, const float* gt, const float* rgb, const float* K, const uint8_t* mask,
-             int B, int H, int W, const cadl_params& p, float* grad, cadl_results* results, const Ws& ws,
-             cudaStream_t st) {
+// Validation + the argument block shared by every phase-B kernel.  Returns CADL_OK with *nothing_to_do set when only
+// metrics (or nothing) were asked for.
+int fill_b_args(PhaseBArgs& a, const float* pred, const float* gt, const float* rgb, const float* K, const uint8_t* mask,
+                int B, int H, int W, const cadl_params& p, float* grad, cadl_results* results, const Ws& ws,
+                bool* nothing_to_do) {
+    *nothing_to_do = false;
     if (!results) return CADL_ERR_NULL;
     const uint32_t t = p.terms & CADL_TERM_ALL;
     if (t == 0) {
-        if (p.metrics) {
-            metrics_finalize_kernel<<<1, 32, 0, st>>>(ws.stats(), p.metrics, results);
-            return cuda_rc(cudaGetLastError());
-        }
+        *nothing_to_do = true;
         return CADL_OK;
     }
     if (!pred) return CADL_ERR_NULL;
@@ -394,7 +443,7 @@ int run_grad(const float* pred, const float* gt, const float* rgb, const float* 
         // avg_pool2d needs at least one output cell at the coarsest scale (torch raises otherwise)
         if ((H >> (p.num_scales - 1)) < 1 || (W >> (p.num_scales - 1)) < 1) return CADL_ERR_SHAPE;
     }
-    PhaseBArgs a{};
+    a = PhaseBArgs{};
     a.pred = pred; a.gt = gt; a.rgb = rgb; a.K = K; a.mask = mask; a.grad = grad;
     a.B = B; a.H = H; a.W = W;
     a.tiles_x = (W + TW - 1) / TW; a.tiles_y = (H + TH - 1) / TH;
@@ -418,6 +467,35 @@ int run_grad(const float* pred, const float* gt, const float* rgb, const float* 
     }
     a.sm_nx = a.inv_nx[0];
     a.sm_ny = a.inv_ny[0];
+    return CADL_OK;
+}
+
+// fast path: aligned shapes (every BASELINE configuration); same values, ~4x fewer instructions
+bool fast_path_ok(const PhaseBArgs& a, const cadl_params& p) {
+    const uint32_t t = a.terms;
+    return a.vec_ok && (a.H % 8 == 0) && (a.W % 8 == 0) && (!(t & CADL_TERM_GRAD) || p.num_scales == 4) &&
+           (!((t & CADL_TERM_SI) && (t & CADL_TERM_GRAD)) || p.eps_si == p.eps_grad) && p.eps_si > 0.f &&
+           p.eps_grad > 0.f && p.eps_si <= 1000.f && p.eps_grad <= 1000.f && !g_force_generic;
+}
+bool stream_path_ok(const PhaseBArgs& a, const cadl_params& p, const Ws& ws) {
+    return fast_path_ok(a, p) && (a.terms & CADL_TERM_GRAD) && ws.has_pyr() && !g_force_tile;
+}
+
+int run_grad(const float* pred, const float* gt, const float* rgb, const float* K, const uint8_t* mask,
+             int B, int H, int W, const cadl_params& p, float* grad, cadl_results* results, const Ws& ws,
+             cudaStream_t st, const StepPlan& plan = StepPlan()) {
+    PhaseBArgs a;
+    bool nothing = false;
+    int rc0 = fill_b_args(a, pred, gt, rgb, K, mask, B, H, W, p, grad, results, ws, &nothing);
+    if (rc0) return rc0;
+    if (nothing) {
+        if (p.metrics) {
+            metrics_finalize_kernel<<<1, 32, 0, st>>>(ws.stats(), p.metrics, results);
+            return cuda_rc(cudaGetLastError());
+        }
+        return CADL_OK;
+    }
+    const uint32_t t = a.terms;
 
     cudaError_t e = cudaSuccess;
     bool offset_done = false;
@@ -441,18 +519,15 @@ int run_grad(const float* pred, const float* gt, const float* rgb, const float* 
         }
         return cuda_rc(e);
     }
-    // fast path: aligned shapes (every BASELINE configuration); same values, ~4x fewer instructions
-    const bool fast = a.vec_ok && (H % 8 == 0) && (W % 8 == 0) && (!(t & CADL_TERM_GRAD) || p.num_scales == 4) &&
-                      (!((t & CADL_TERM_SI) && (t & CADL_TERM_GRAD)) || p.eps_si == p.eps_grad) && p.eps_si > 0.f &&
-                      p.eps_grad > 0.f && p.eps_si <= 1000.f && p.eps_grad <= 1000.f && !g_force_generic;
+    const bool fast = fast_path_ok(a, p);
     if (fast) {
         a.tiles_x = (W + FTW - 1) / FTW; a.tiles_y = (H + FTH - 1) / FTH;
         a.b_rows = a.tiles_x * a.tiles_y * B;
-        const bool stream = (t & CADL_TERM_GRAD) && ws.has_pyr() && !g_force_tile;
+        const bool stream = stream_path_ok(a, p, ws);
         switch (t) {
-            case CADL_TERM_ALL: e = stream ? launch_stream<15>(a, ws, st, &offset_done) : launch_fast<15>(a, st); break;
-            case CADL_TERM_SI | CADL_TERM_GRAD | CADL_TERM_SMOOTH: e = stream ? launch_stream<7>(a, ws, st, &offset_done) : launch_fast<7>(a, st); break;
-            case CADL_TERM_GRAD: e = stream ? launch_stream<FB_GRAD>(a, ws, st, &offset_done) : launch_fast<FB_GRAD>(a, st); break;
+            case CADL_TERM_ALL: e = stream ? launch_stream<15>(a, ws, st, &offset_done, plan) : launch_fast<15>(a, st); break;
+            case CADL_TERM_SI | CADL_TERM_GRAD | CADL_TERM_SMOOTH: e = stream ? launch_stream<7>(a, ws, st, &offset_done, plan) : launch_fast<7>(a, st); break;
+            case CADL_TERM_GRAD: e = stream ? launch_stream<FB_GRAD>(a, ws, st, &offset_done, plan) : launch_fast<FB_GRAD>(a, st); break;
             case CADL_TERM_SMOOTH: e = launch_fast<FB_SMOOTH>(a, st); break;
             default: return CADL_ERR_UNSUPPORTED;
         }
@@ -521,6 +596,7 @@ void cadl_debug_force_generic(int on) {
     g_force_no_tma = (on >> 1) & 1;
     g_force_tile = (on >> 3) & 1;
     g_no_pdl = (on >> 4) & 1;
+    g_no_overlap = (on >> 5) & 1;
     g_use_ws = (on >> 2) & 1;
 }
 size_t cadl_sizeof_params(void) { return sizeof(cadl_params); }
@@ -591,11 +667,40 @@ int cadl_stack_fwd_bwd(const float* pred, const float* gt, const float* rgb, con
     int rc = check_common(B, H, W, workspace, workspace_bytes);
     if (rc) return rc;
     Ws ws = make_ws(workspace, B, H, W);
-    kt_mark((cudaStream_t)stream, "start");
-    rc = run_reduce(pred, gt, mask, B, H, W, *params, ws, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    kt_mark(st, "start");
+    // Streaming path with a phase A: the pooled-pyramid kernels go FIRST, onto the auxiliary stream, as one
+    // persistent CTA per SM; phase A follows on the caller's stream with a grid that leaves them room.
+    StepPlan plan;
+    AuxStream* aux = nullptr;
+    if (!g_no_overlap && !g_kt.on && phase_a_flags(*params) != 0 && results) {
+        PhaseBArgs a;
+        bool nothing = false;
+        if (fill_b_args(a, pred, gt, rgb, K, mask, B, H, W, *params, grad_pred, results, ws, &nothing) == CADL_OK && !nothing &&
+            stream_path_ok(a, *params, ws) && (aux = aux_for_current_device()) != nullptr) {
+            const int sms = num_sms_cached();
+            // two pyramid CTAs per SM, the rest of the 4-CTA wave for phase A (measured at config 3, us/step:
+            // 222 CTAs 207.4, 260 202.0, 280 195.2, 296 196.2, 330 198.9, 370 214.8; in line on one stream 208.7)
+            const int pyr_ctas = 2 * sms;
+            plan.pyr_grid = ws.L.pyr_blocks < pyr_ctas ? ws.L.pyr_blocks : pyr_ctas;
+            plan.a_blocks_per_img = (4 * sms - plan.pyr_grid) / B;       // phase A: 4 CTAs of 256 threads per SM
+            if (plan.a_blocks_per_img < 1) plan.a_blocks_per_img = 1;
+            cudaError_t e = cudaEventRecord(aux->fork, st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(aux->s2, aux->fork, 0);
+            if (e == cudaSuccess) e = launch_pyramid(a, ws, aux->s2, plan.pyr_grid, false, !g_no_pdl);
+            if (e == cudaSuccess) e = cudaEventRecord(aux->join, aux->s2);
+            if (e != cudaSuccess) return cuda_rc(e);
+            plan.pyr_prelaunched = true;
+        }
+    }
+    rc = run_reduce(pred, gt, mask, B, H, W, *params, ws, st, plan);
     if (rc) return rc;
-    kt_mark((cudaStream_t)stream, "phase_a_kernel");
-    rc = run_grad(pred, gt, rgb, K, mask, B, H, W, *params, grad_pred, results, ws, (cudaStream_t)stream);
+    kt_mark(st, "phase_a_kernel");
+    if (plan.pyr_prelaunched) {
+        cudaError_t e = cudaStreamWaitEvent(st, aux->join, 0);
+        if (e != cudaSuccess) return cuda_rc(e);
+    }
+    rc = run_grad(pred, gt, rgb, K, mask, B, H, W, *params, grad_pred, results, ws, st, plan);
     kt_mark((cudaStream_t)stream, "end");
     kt_finish();
     return rc;

@@ -50,12 +50,13 @@ __global__ void __launch_bounds__(256) pyr_pool_kernel(const float* __restrict__
     // which wait for THIS grid, also see phase A's statistics.
     pdl_trigger();
     const int W8 = W >> 3, H8 = H >> 3;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     // the streaming kernel's per-image completion counters (stream-ordered before it; their offset depends on the
     // shape, and one workspace serves calls of different shapes)
     if (blockIdx.x == 0)
         for (int i = threadIdx.x; i < B; i += blockDim.x) img_cnt[i] = 0u;
-    if (idx >= B * H8 * W8) { pdl_wait(); return; }
+    // grid-stride over the 8x8 blocks: the grid is either one thread per block or, when the kernel runs beside
+    // phase A on a second stream, one CTA per SM
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < B * H8 * W8; idx += gridDim.x * blockDim.x) {
     const int bx = idx % W8, by = (idx / W8) % H8, b = idx / (W8 * H8);
     const float* pp = pred + (size_t)b * H * W + (size_t)(by * 8) * W + bx * 8;
     const float* gp = gt + (size_t)b * H * W + (size_t)(by * 8) * W + bx * 8;
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(256) pyr_pool_kernel(const float* __restrict__
         py.lg[2][o] = l.y;
         py.rq[2][o] = in_range_pos(q, eps, 1000.0f) ? rcp_approx(q) : 0.f;
     }
+    }   // blocks
     pdl_wait();
 }
 
@@ -207,9 +209,8 @@ __global__ void __launch_bounds__(256) pyr_coef_kernel(const PyrCoefArgs a) {
     pdl_wait();        // the pooled arrays of pyr_pool_kernel
     pdl_trigger();
     const int W8 = a.W >> 3, H8 = a.H >> 3;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // GX1, GY1, GX2, GY2, GX3, GY3
-    if (idx < a.B * H8 * W8) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < a.B * H8 * W8; idx += gridDim.x * blockDim.x) {
         const int bx = idx % W8, by = (idx / W8) % H8, b = idx / (W8 * H8);
         const int H1 = a.H >> 1, W1 = a.W >> 1, H2 = a.H >> 2, W2 = a.W >> 2, H3 = a.H >> 3, W3 = a.W >> 3;
         float c3[1][1], c2[2][2], c1[4][4];

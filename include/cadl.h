@@ -96,8 +96,9 @@ const char* cadl_error_string(int code);
 /* Test hook (bit mask): 1 = always take the generic phase-B kernel (any shape/alignment) instead of the
  * aligned fast path; 8 = fast path as ONE tile kernel (cadl_phase_b_fast.cuh) instead of the streaming split
  * (cadl_phase_b_stream.cuh); together with 8: 2 = stage tiles with cp.async instead of TMA, 4 = warp-specialised
- * persistent tile kernel (cadl_phase_b_ws.cuh).  All variants must produce the same values.  Process-global;
- * not for production use. */
+ * persistent tile kernel (cadl_phase_b_ws.cuh); 16 = no programmatic dependent launch; 32 = the pooled-pyramid
+ * kernels in line on the caller's stream instead of beside phase A on the auxiliary stream.  All variants must
+ * produce the same values.  Process-global; not for production use. */
 void cadl_debug_force_generic(int on);
 /* Debug trace of the streaming phase-B kernel: while dev_buf is non-NULL every warp (global index < capacity_warps)
  * writes {SM id, start globaltimer ns, end globaltimer ns, work items processed} as 4 x uint64 at dev_buf[4*warp].

@@ -388,9 +388,9 @@ cudaError_t launch_point_fast(PhaseBArgs& a, cudaStream_t st) {
     if (bpi < 1) bpi = 1;
     dim3 grid(bpi, a.B);
     a.b_rows = bpi * a.B;
-    if (a.mask) phase_b_point_fast_kernel<F, true><<<grid, kThreadsB, 0, st>>>(a);
-    else phase_b_point_fast_kernel<F, false><<<grid, kThreadsB, 0, st>>>(a);
-    return cudaGetLastError();
+    const bool pdl = !g_no_pdl && !g_kt.on;
+    if (a.mask) return launch_pdl(phase_b_point_fast_kernel<F, true>, grid, dim3(kThreadsB), st, pdl, a);
+    return launch_pdl(phase_b_point_fast_kernel<F, false>, grid, dim3(kThreadsB), st, pdl, a);
 }
 
 template <int F>

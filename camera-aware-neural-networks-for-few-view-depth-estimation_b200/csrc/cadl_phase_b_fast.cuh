@@ -704,6 +704,7 @@ __global__ void __launch_bounds__(kThreadsB, 4) phase_b_point_fast_kernel(const 
     constexpr bool SI = (F & FB_SI) != 0, RP = (F & FB_RP) != 0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float up = a.upstream;
+    pdl_wait();        // launched behind phase A with programmatic stream serialization: its statistics
     if (tid == 0) {
         const double n = a.stats[ST_SI_N], S = a.stats[ST_SI_S], nr = a.stats[ST_RP_N];
         s_c[0] = n > 0.0 ? (float)(2.0 / n) * a.w_si * up : 0.f;

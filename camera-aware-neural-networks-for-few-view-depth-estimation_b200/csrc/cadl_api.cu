@@ -683,7 +683,9 @@ int cadl_stack_fwd_bwd(const float* pred, const float* gt, const float* rgb, con
             // 222 CTAs 207.4, 260 202.0, 280 195.2, 296 196.2, 330 198.9, 370 214.8; in line on one stream 208.7)
             const int pyr_ctas = 2 * sms;
             plan.pyr_grid = ws.L.pyr_blocks < pyr_ctas ? ws.L.pyr_blocks : pyr_ctas;
-            plan.a_blocks_per_img = (4 * sms - plan.pyr_grid) / B;       // phase A: 4 CTAs of 256 threads per SM
+            // phase A: 4 CTAs of 256 threads per SM; everything must fit ONE wave (more, shorter phase-A blocks
+            // starve the pyramid: 13 blocks per image 207.0 us/step, 18: 204.8, 36: 208.7 against 9: 196.5)
+            plan.a_blocks_per_img = (4 * sms - plan.pyr_grid) / B;
             if (plan.a_blocks_per_img < 1) plan.a_blocks_per_img = 1;
             cudaError_t e = cudaEventRecord(aux->fork, st);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(aux->s2, aux->fork, 0);

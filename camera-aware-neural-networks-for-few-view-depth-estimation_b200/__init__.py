@@ -65,6 +65,7 @@ ABI_SYMBOLS = (
     "cadl_scale_grad", "cadl_metrics", "cadl_rays_from_K", "cadl_photometric_fwd_bwd",
     "cadl_batch_prep", "cadl_clip_workspace_bytes", "cadl_clip_grad_norm", "cadl_debug_set_trace",
     "cadl_debug_kernel_times",
+    "cadl_batch_augment", "cadl_accumulate",
 )
 
 _lib = None
@@ -334,6 +335,33 @@ def batch_prep(rgb, depth, K, H: int, W: int):
                                    _stream(rgb))
     _check(rc, "cadl_batch_prep")
     return rgb_o, dep_o, K_o
+
+
+def batch_augment(rgb, depth, K, aug, H: int, W: int):
+    """augmentSample + resize on the device; aug: (B, 8) float32 CUDA tensor (see include/cadl.h: cadl_batch_augment)."""
+    _require_cuda(rgb, depth, K, aug)
+    B, _, h, w = rgb.shape
+    assert aug.shape == (B, 8) and aug.dtype == torch.float32 and aug.is_contiguous()
+    rgb_o = torch.empty(B, 3, H, W, dtype=torch.float32, device=rgb.device)
+    dep_o = torch.empty(B, 1, H, W, dtype=torch.float32, device=rgb.device)
+    K_o = torch.empty(B, 3, 3, dtype=torch.float32, device=rgb.device)
+    with torch.cuda.device(rgb.device):
+        rc = lib().cadl_batch_augment(_ptr(rgb), _ptr(depth), _ptr(K), _ptr(aug), B, h, w, H, W, _ptr(rgb_o), _ptr(dep_o),
+                                      _ptr(K_o), _stream(rgb))
+    _check(rc, "cadl_batch_augment")
+    return rgb_o, dep_o, K_o
+
+
+def accumulate(values, weight: float, acc):
+    """acc[:n] += weight * values, acc[n] += weight, on the device (no host sync)."""
+    _require_cuda(values, acc)
+    n = values.numel()
+    assert values.dtype == torch.float32 and acc.dtype == torch.float64 and acc.numel() >= n + 1
+    L = lib()
+    L.cadl_accumulate.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+    with torch.cuda.device(values.device):
+        rc = L.cadl_accumulate(_ptr(values), n, float(weight), _ptr(acc), _stream(values))
+    _check(rc, "cadl_accumulate")
 
 
 class GradClipper:

@@ -799,8 +799,23 @@ int cadl_batch_prep(const float* rgb_in, const float* depth_in, const float* K_i
                     float* rgb_out, float* depth_out, float* K_out, cadl_stream_t stream) {
     if (!rgb_in || !depth_in || !K_in || !rgb_out || !depth_out || !K_out) return CADL_ERR_NULL;
     if (B < 1 || h < 1 || w < 1 || H < 1 || W < 1 || H > 65535 || B > 65535) return CADL_ERR_SHAPE;
-    PrepArgs a{rgb_in, depth_in, K_in, rgb_out, depth_out, K_out, B, h, w, H, W};
+    PrepArgs a{rgb_in, depth_in, K_in, rgb_out, depth_out, K_out, B, h, w, H, W, nullptr};
     return cuda_rc(launch_batch_prep(a, (cudaStream_t)stream));
+}
+
+int cadl_batch_augment(const float* rgb_in, const float* depth_in, const float* K_in, const float* aug_dev, int B, int h,
+                       int w, int H, int W, float* rgb_out, float* depth_out, float* K_out, cadl_stream_t stream) {
+    if (!rgb_in || !depth_in || !K_in || !rgb_out || !depth_out || !K_out || !aug_dev) return CADL_ERR_NULL;
+    if (B < 1 || h < 1 || w < 1 || H < 1 || W < 1 || H > 65535 || B > 65535) return CADL_ERR_SHAPE;
+    PrepArgs a{rgb_in, depth_in, K_in, rgb_out, depth_out, K_out, B, h, w, H, W, aug_dev};
+    return cuda_rc(launch_batch_prep(a, (cudaStream_t)stream));
+}
+
+int cadl_accumulate(const float* values_dev, int n, double weight, double* acc_dev, cadl_stream_t stream) {
+    if (!values_dev || !acc_dev) return CADL_ERR_NULL;
+    if (n < 1) return CADL_ERR_SHAPE;
+    accumulate_kernel<<<(n + 1 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(values_dev, n, weight, acc_dev);
+    return cuda_rc(cudaGetLastError());
 }
 
 size_t cadl_clip_workspace_bytes(void) { return 256 + sizeof(double) * 148 * 8; }

@@ -24,28 +24,56 @@ struct PrepArgs {
     float* depth_out;       // (B,1,H,W)
     float* K_out;           // (B,3,3)
     int B, h, w, H, W;
+    // optional per-image augmentation (B, CADL_AUG_STRIDE) floats, the loader's augmentSample
+    // (src/data/sunrgbd_loader.cpp:352-384) composed with the resize that follows it (:161-166):
+    //   [0..3] crop_x, crop_y, crop_w, crop_h  (applyCrop :388-415; crop_w == 0: no crop)
+    //   [4]    horizontal flip != 0             (applyHorizontalFlip :417-432)
+    //   [5]    colour jitter != 0, [6] contrast factor, [7] brightness factor   (applyColorJitter :434-443)
+    const float* aug;
 };
 
 __global__ void __launch_bounds__(256) batch_prep_kernel(const PrepArgs a) {
     const int b = blockIdx.z;
     const int y = blockIdx.y;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    // the region of the input that is resized: the whole image, or the crop window
+    int cx0 = 0, cy0 = 0, cw = a.w, ch = a.h;
+    bool flip = false, jitter = false;
+    float contrast = 1.f, brightness = 1.f;
+    if (a.aug) {
+        const float* g = a.aug + (size_t)b * 8;
+        if (__ldg(g + 2) > 0.f) { cx0 = (int)__ldg(g + 0); cy0 = (int)__ldg(g + 1); cw = (int)__ldg(g + 2); ch = (int)__ldg(g + 3); }
+        flip = __ldg(g + 4) != 0.f;
+        jitter = __ldg(g + 5) != 0.f;
+        contrast = __ldg(g + 6);
+        brightness = __ldg(g + 7);
+    }
     if (x == 0 && y == 0) {
-        // sunrgbd_loader.cpp:480-488: fx, cx scale with W; fy, cy with H
-        const float sx = (float)a.W / (float)a.w, sy = (float)a.H / (float)a.h;
         const float* Ki = a.K_in + (size_t)b * 9;
         float* Ko = a.K_out + (size_t)b * 9;
+        float k[9];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) Ko[i] = Ki[i];
-        Ko[0] = Ki[0] * sx; Ko[4] = Ki[4] * sy; Ko[2] = Ki[2] * sx; Ko[5] = Ki[5] * sy;
+        for (int i = 0; i < 9; ++i) k[i] = Ki[i];
+        if (a.aug && __ldg(a.aug + (size_t)b * 8 + 2) > 0.f) {   // :411-414  principal point follows the crop
+            k[2] = k[2] - (float)cx0;
+            k[5] = k[5] - (float)cy0;
+        }
+        if (flip) k[2] = ((float)cw - k[2]) - 1.0f;               // :428-431  W - cx - 1
+        // sunrgbd_loader.cpp:480-488: fx, cx scale with W; fy, cy with H
+        const float sx = (float)a.W / (float)cw, sy = (float)a.H / (float)ch;
+        k[0] = k[0] * sx; k[4] = k[4] * sy; k[2] = k[2] * sx; k[5] = k[5] * sy;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Ko[i] = k[i];
     }
     if (x >= a.W) return;
-    const float scale_h = (float)a.h / (float)a.H, scale_w = (float)a.w / (float)a.W;
+    const float scale_h = (float)ch / (float)a.H, scale_w = (float)cw / (float)a.W;
+    // column of the (cropped, flipped) image -> column of the input
+    auto col = [&](int xc) { return cx0 + (flip ? cw - 1 - xc : xc); };
     // nearest (depth): sunrgbd_loader.cpp:461-467
     {
-        const int sy = min((int)floorf((float)y * scale_h), a.h - 1);
-        const int sx = min((int)floorf((float)x * scale_w), a.w - 1);
-        a.depth_out[((size_t)b * a.H + y) * a.W + x] = __ldg(a.depth_in + ((size_t)b * a.h + sy) * a.w + sx);
+        const int sy = min((int)floorf((float)y * scale_h), ch - 1);
+        const int sx = min((int)floorf((float)x * scale_w), cw - 1);
+        a.depth_out[((size_t)b * a.H + y) * a.W + x] = __ldg(a.depth_in + ((size_t)b * a.h + cy0 + sy) * a.w + col(sx));
     }
     // bilinear (rgb): sunrgbd_loader.cpp:453-459
     float fy = scale_h * ((float)y + 0.5f) - 0.5f;
@@ -53,16 +81,34 @@ __global__ void __launch_bounds__(256) batch_prep_kernel(const PrepArgs a) {
     fy = fy < 0.f ? 0.f : fy;
     fx = fx < 0.f ? 0.f : fx;
     const int y0 = (int)fy, x0 = (int)fx;
-    const int y1 = y0 + (y0 < a.h - 1 ? 1 : 0), x1 = x0 + (x0 < a.w - 1 ? 1 : 0);
+    const int y1 = y0 + (y0 < ch - 1 ? 1 : 0), x1 = x0 + (x0 < cw - 1 ? 1 : 0);
     const float ly1 = fy - (float)y0, lx1 = fx - (float)x0;
     const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const int c0 = col(x0), c1 = col(x1);
+    // colour jitter acts on the pixels before the resize: clamp(rgb * contrast + brightness - 1, 0, 1), one rounding per op
+    auto tap = [&](const float* src, int yy, int xx) {
+        float v = __ldg(src + (size_t)(cy0 + yy) * a.w + xx);
+        if (jitter) {
+            v = __fadd_rn(__fadd_rn(__fmul_rn(v, contrast), brightness), -1.0f);
+            v = clamp_nan(v, 0.f, 1.f);
+        }
+        return v;
+    };
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const float* src = a.rgb_in + ((size_t)b * 3 + c) * a.h * a.w;
-        const float v = ly0 * (lx0 * __ldg(src + (size_t)y0 * a.w + x0) + lx1 * __ldg(src + (size_t)y0 * a.w + x1)) +
-                        ly1 * (lx0 * __ldg(src + (size_t)y1 * a.w + x0) + lx1 * __ldg(src + (size_t)y1 * a.w + x1));
+        const float v = ly0 * (lx0 * tap(src, y0, c0) + lx1 * tap(src, y0, c1)) +
+                        ly1 * (lx0 * tap(src, y1, c0) + lx1 * tap(src, y1, c1));
         a.rgb_out[(((size_t)b * 3 + c) * a.H + y) * a.W + x] = v;
     }
+}
+
+// acc[i] += weight * values[i] (i < n), acc[n] += weight: device-resident running sums of per-batch scalars
+// (the trainers' `metrics.loss += loss.item<float>() * batch_size`, production_trainer.h:213-216, without the sync)
+__global__ void accumulate_kernel(const float* values, int n, double weight, double* acc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) acc[i] += weight * (double)values[i];
+    else if (i == n) acc[n] += weight;
 }
 
 inline cudaError_t launch_batch_prep(const PrepArgs& a, cudaStream_t st) {

@@ -59,6 +59,7 @@ class StepHarness:
         if hasattr(L, "cadh_clip_grad_norm"):        # drop-in build only ("next" rows)
             L.cadh_clip_grad_norm.argtypes = [C.c_int, C.c_int, vp, vp, C.c_float, C.c_int, vp, vp, C.c_char_p, C.c_int]
             L.cadh_batch_prep.argtypes = [C.c_int] * 6 + [vp] * 6 + [C.c_char_p, C.c_int]
+            L.cadh_accumulate.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_char_p, C.c_int]
         self.L = L
 
     # ------------------------------------------------------------------
@@ -151,6 +152,17 @@ class StepHarness:
         if rc:
             self._raise(err)
         return float(out2[0]), float(out2[1]), outs
+
+    def accumulate(self, device: int, values, weights) -> float:
+        """DeviceAccumulator (host/training/loss_accumulator.h): weighted mean of per-batch losses."""
+        v = np.ascontiguousarray(values, dtype=np.float32)
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        out = C.c_double(0.0)
+        err = C.create_string_buffer(2048)
+        rc = self.L.cadh_accumulate(device, len(v), _p(v), w.ctypes.data_as(C.c_void_p), C.byref(out), err, len(err))
+        if rc:
+            self._raise(err)
+        return float(out.value)
 
     def batch_prep(self, device: int, rgb, depth, K, H: int, W: int):
         """resizeBatchOnDevice (host/data/batch_prep.h)."""

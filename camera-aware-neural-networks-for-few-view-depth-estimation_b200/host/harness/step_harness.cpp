@@ -31,6 +31,7 @@
 #ifdef CADL_DROPIN
 #include "training/validation_metrics.h"
 #include "training/grad_clip.h"
+#include "training/loss_accumulator.h"
 #include "data/batch_prep.h"
 #endif
 
@@ -385,6 +386,20 @@ int cadh_clip_grad_norm(int device, int count, const float* const* grads_host, c
             auto g = params[i].grad().to(torch::kCPU).contiguous();
             std::memcpy(grads_out_host[i], g.data_ptr<float>(), sizeof(float) * g.numel());
         }
+        return 0;
+    } catch (const std::exception& e) {
+        return fail(err, errlen, e);
+    }
+}
+
+// DeviceAccumulator over `batches` loss values with weights: returns the weighted mean (one sync at the end)
+int cadh_accumulate(int device, int batches, const float* values, const double* weights, double* mean_out, char* err,
+                    int errlen) {
+    try {
+        auto dev = pick_device(device);
+        DeviceAccumulator acc(1);
+        for (int i = 0; i < batches; ++i) acc.add(torch::full({1}, values[i], torch::TensorOptions().device(dev)), weights[i]);
+        *mean_out = acc.mean()[0];
         return 0;
     } catch (const std::exception& e) {
         return fail(err, errlen, e);

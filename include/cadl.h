@@ -193,6 +193,24 @@ int cadl_rays_from_K(const float* K, int k_batched, const float* pose, int B, in
 int cadl_batch_prep(const float* rgb_in, const float* depth_in, const float* K_in, int B, int h, int w, int H, int W,
                     float* rgb_out, float* depth_out, float* K_out, cadl_stream_t stream);
 
+/* The loader's augmentSample + the resize that follows it (src/data/sunrgbd_loader.cpp:352-384, :161-166) for a whole
+ * batch in the same single launch.  aug_dev: (B, CADL_AUG_STRIDE) floats per image, drawn by the host RNG exactly as
+ * the loader draws them:
+ *   [0..3] crop_x, crop_y, crop_w, crop_h in input pixels (applyCrop :388-415; crop_w == 0: no crop)
+ *   [4]    != 0: horizontal flip (applyHorizontalFlip :417-432)
+ *   [5]    != 0: colour jitter clamp(rgb * [6] + [7] - 1, 0, 1) applied before the resize (applyColorJitter :434-443)
+ * K follows: cx -= crop_x, cy -= crop_y; flip: cx = crop_w - cx - 1; then the resize scaling.  (The per-sample ray
+ * maps the loader also crops/flips/resizes are regenerated from the final K with cadl_rays_from_K instead.) */
+#define CADL_AUG_STRIDE 8
+int cadl_batch_augment(const float* rgb_in, const float* depth_in, const float* K_in, const float* aug_dev, int B, int h,
+                       int w, int H, int W, float* rgb_out, float* depth_out, float* K_out, cadl_stream_t stream);
+
+/* Device-resident running sums of per-batch scalars: acc_dev[i] += weight * values_dev[i] for i < n and
+ * acc_dev[n] += weight (acc_dev: n + 1 doubles the caller zeroed).  Replaces the trainers'
+ * `metrics.loss += loss.item<float>() * batch_size` (src/training/production_trainer.h:213-216,
+ * tensorboard_trainer_enhanced.h:307,363) and its host sync per batch: read the sums once per epoch. */
+int cadl_accumulate(const float* values_dev, int n, double weight, double* acc_dev, cadl_stream_t stream);
+
 /* torch::nn::utils::clip_grad_norm_(params, max_norm) and the trainers' computeGradientNorm
  * (src/training/tensorboard_trainer_enhanced.h:300-302, :560-571) over `count` gradient tensors without a host
  * sync.  grad_ptrs_dev / sizes_dev: device arrays of pointers and element counts; chunk_prefix_dev: device

@@ -310,6 +310,29 @@ def resize_sample(rgb, depth, K, H: int, W: int):
     return rgb2, depth2, K2
 
 
+def augment_resize_sample(rgb, depth, K, aug, H: int, W: int):
+    """SunRGBDLoader::augmentSample followed by resizeSample, one sample      reference src/data/sunrgbd_loader.cpp:352-384,161-166
+    rgb (3,h,w), depth (1,h,w), K (3,3); aug = [crop_x, crop_y, crop_w, crop_h, flip, jitter, contrast, brightness]."""
+    cx, cy, cw, ch = (int(v) for v in aug[:4])
+    K = K.clone()
+    if cw > 0:                                                                         # applyCrop :388-415
+        rgb = rgb[:, cy:cy + ch, cx:cx + cw]
+        depth = depth[:, cy:cy + ch, cx:cx + cw]
+        K[0, 2] = K[0, 2] - cx                                                         # :412
+        K[1, 2] = K[1, 2] - cy                                                         # :413
+    if aug[4] != 0:                                                                    # applyHorizontalFlip :417-432
+        rgb = torch.flip(rgb, [2])
+        depth = torch.flip(depth, [2])
+        Wc = rgb.shape[2]
+        K[0, 2] = torch.tensor(float(Wc), dtype=torch.float32) - K[0, 2] - 1           # :430  W - cx - 1
+    if aug[5] != 0:                                                                    # applyColorJitter :434-443
+        c = torch.tensor(float(aug[6]), dtype=torch.float32)
+        bconst = torch.tensor(float(aug[7]), dtype=torch.float32)
+        rgb = torch.clamp(rgb * c + bconst - 1.0, 0.0, 1.0)                            # :442
+    r, d, k = resize_sample(rgb[None].contiguous(), depth[None].contiguous(), K[None], H, W)
+    return r[0], d[0], k[0]
+
+
 def clip_grad_norm(grads, max_norm: float):
     """torch::nn::utils::clip_grad_norm_ (tensorboard_trainer_enhanced.h:300-302) and computeGradientNorm (:560-571).
     Returns (total_norm, clipped grads)."""

@@ -139,3 +139,12 @@ def test_batch_prep_cpp_wrapper(pkg, host):
     np.testing.assert_allclose(ro, r.numpy(), rtol=0, atol=2e-6)
     assert np.array_equal(do, d.numpy())
     np.testing.assert_allclose(ko, k.numpy(), rtol=1e-6)
+
+
+def test_device_accumulator_cpp_wrapper(host):
+    """host/training/loss_accumulator.h: `metrics.loss += loss.item<float>() * batch_size` without the per-batch sync."""
+    vals = np.array([0.5, 0.25, 1.5, 2.0], np.float32)
+    w = np.array([32, 32, 32, 7], np.float64)
+    got = host.accumulate(0, vals, w)
+    ref = float((vals.astype(np.float64) * w).sum() / w.sum())
+    assert abs(got - ref) <= 1e-12 * abs(ref)

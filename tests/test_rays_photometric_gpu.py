@@ -156,3 +156,46 @@ def test_clip_grad_norm_matches_torch(pkg, oracle):
     keep = grads[0].clone()
     out = pkg.GradClipper(grads)(0.1, clip=False).cpu()
     assert torch.equal(grads[0], keep) and rel_err(float(out[0]), float(keep.double().norm())) <= 1e-6
+
+
+def test_batch_augment_matches_loader_restatement(pkg, oracle):
+    """augmentSample (crop, flip, colour jitter) + the resize after it, per image, against the op-for-op restatement."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(11)
+    B, h, w, H, W = 6, 48, 64, 48, 64
+    rgb = torch.rand(B, 3, h, w, generator=g)
+    depth = torch.rand(B, 1, h, w, generator=g) * 9 + 0.3
+    K = torch.tensor([[55.0, 0, 31.5], [0, 56.0, 23.5], [0, 0, 1]]).repeat(B, 1, 1) * (1 + 0.01 * torch.arange(B).view(B, 1, 1))
+    K[:, 2, 2] = 1
+    aug = torch.tensor([
+        [0, 0, 0, 0, 0, 0, 1.0, 1.0],            # identity
+        [5, 3, 51, 38, 0, 0, 1.0, 1.0],          # crop (scale 0.8)
+        [0, 0, 0, 0, 1, 0, 1.0, 1.0],            # flip
+        [0, 0, 0, 0, 0, 1, 1.13, 0.91],          # colour jitter
+        [9, 7, 44, 33, 1, 1, 0.87, 1.08],        # all three
+        [12, 9, 38, 28, 1, 0, 1.0, 1.0],
+    ], dtype=torch.float32)
+    ro, do, Ko = pkg.batch_augment(rgb.to(dev), depth.to(dev), K.to(dev), aug.to(dev), H, W)
+    for b in range(B):
+        r, d, k = oracle.augment_resize_sample(rgb[b], depth[b], K[b], aug[b].tolist(), H, W)
+        assert float((ro[b].cpu() - r).abs().max()) <= 2e-6, b
+        assert torch.equal(do[b].cpu(), d), b
+        assert torch.allclose(Ko[b].cpu(), k, rtol=1e-6, atol=0), (b, Ko[b].cpu(), k)
+    # no augmentation == cadl_batch_prep
+    r0, d0, K0 = pkg.batch_prep(rgb.to(dev), depth.to(dev), K.to(dev), 40, 56)
+    z = torch.zeros(B, 8); z[:, 6:] = 1
+    r1, d1, K1 = pkg.batch_augment(rgb.to(dev), depth.to(dev), K.to(dev), z.to(dev), 40, 56)
+    assert torch.equal(r0, r1) and torch.equal(d0, d1) and torch.equal(K0, K1)
+
+
+def test_device_accumulator(pkg):
+    """cadl_accumulate: batch-size-weighted running sums without a host sync (production_trainer.h:213-216)."""
+    dev = torch.device("cuda:0")
+    acc = torch.zeros(4, dtype=torch.float64, device=dev)
+    vals = [torch.tensor([0.5, 1.25, 3.0]), torch.tensor([0.25, 2.0, 1.0]), torch.tensor([1.5, 0.75, 2.5])]
+    ws = [32, 32, 7]
+    for v, w in zip(vals, ws):
+        pkg.accumulate(v.to(dev), w, acc)
+    ref = sum(w * v.double() for v, w in zip(vals, ws))
+    out = acc.cpu()
+    assert torch.equal(out[:3], ref) and float(out[3]) == float(sum(ws))

@@ -211,6 +211,7 @@ def main():
 
     def step():
         if args.mode == "global" and world > 1:
+            pkg.stack_prepare(pred, gt, params, ws)          # pyramid kernels beside phase A and the all-reduce
             pkg.stack_reduce(pred, gt, None, params, ws)
             dist.all_reduce(ws.stats_view())                 # 32 doubles over NVLink (NCCL), stream-ordered
             pkg.stack_grad(pred, gt, rgb, K, None, params, grad, ws)

@@ -40,6 +40,7 @@ class CadlParams(C.Structure):
         ("min_depth", C.c_float), ("max_depth", C.c_float),
         ("upstream", C.c_float),
         ("global_B", C.c_int32),
+        ("pyramid_prepared", C.c_int32),
     ]
 
 
@@ -65,7 +66,7 @@ ABI_SYMBOLS = (
     "cadl_scale_grad", "cadl_metrics", "cadl_rays_from_K", "cadl_photometric_fwd_bwd",
     "cadl_batch_prep", "cadl_clip_workspace_bytes", "cadl_clip_grad_norm", "cadl_debug_set_trace",
     "cadl_debug_kernel_times",
-    "cadl_batch_augment", "cadl_accumulate",
+    "cadl_batch_augment", "cadl_accumulate", "cadl_stack_prepare",
 )
 
 _lib = None
@@ -215,6 +216,21 @@ def stack_fwd_bwd(pred, gt, rgb, K, mask=None, params: Optional[CadlParams] = No
                                       _ptr(ws.grad), _ptr(ws.results), _ptr(ws.buf), ws.bytes, _stream(pred))
     _check(rc, "cadl_stack_fwd_bwd")
     return ws
+
+
+def stack_prepare(pred, gt, params: CadlParams, ws: Workspace) -> bool:
+    """Split API: start the pooled-pyramid kernels beside stack_reduce / the all-reduce.  Sets
+    ``params.pyramid_prepared`` and returns True when the streaming path applies, else leaves it 0."""
+    _require_cuda(pred, gt)
+    B, _, H, W = pred.shape
+    params.pyramid_prepared = 0
+    with torch.cuda.device(pred.device):
+        rc = lib().cadl_stack_prepare(_ptr(pred), _ptr(gt), B, H, W, C.byref(params), _ptr(ws.buf), ws.bytes, _stream(pred))
+    if rc == 4:      # CADL_ERR_UNSUPPORTED: the generic / tile path will run, nothing to prepare
+        return False
+    _check(rc, "cadl_stack_prepare")
+    params.pyramid_prepared = 1
+    return True
 
 
 def stack_reduce(pred, gt, mask, params: CadlParams, ws: Workspace):

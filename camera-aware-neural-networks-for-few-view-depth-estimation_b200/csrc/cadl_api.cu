@@ -399,6 +399,29 @@ cudaError_t launch_point(const PhaseBArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// Grid split when the pyramid kernels run beside phase A: two pyramid CTAs per SM, the rest of the 4-CTA wave for
+// phase A (measured at config 3, us/step: 222 pyramid CTAs 207.4, 260 202.0, 280 195.2, 296 196.2, 330 198.9,
+// 370 214.8; in line on one stream 208.7).  Everything must fit ONE wave: more, shorter phase-A blocks starve the
+// pyramid (13 blocks per image 207.0 us/step, 18: 204.8, 36: 208.7 against 9: 196.5).
+StepPlan concurrent_plan(const Ws& ws, int B) {
+    StepPlan plan;
+    const int sms = num_sms_cached();
+    const int pyr_ctas = 2 * sms;
+    plan.pyr_grid = ws.L.pyr_blocks < pyr_ctas ? ws.L.pyr_blocks : pyr_ctas;
+    plan.a_blocks_per_img = (4 * sms - plan.pyr_grid) / B;       // phase A: 4 CTAs of 256 threads per SM
+    if (plan.a_blocks_per_img < 1) plan.a_blocks_per_img = 1;
+    plan.pyr_prelaunched = true;
+    return plan;
+}
+
+cudaError_t prelaunch_pyramid(const PhaseBArgs& a, const Ws& ws, cudaStream_t st, AuxStream* aux, const StepPlan& plan) {
+    cudaError_t e = cudaEventRecord(aux->fork, st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(aux->s2, aux->fork, 0);
+    if (e == cudaSuccess) e = launch_pyramid(a, ws, aux->s2, plan.pyr_grid, false, !g_no_pdl);
+    if (e == cudaSuccess) e = cudaEventRecord(aux->join, aux->s2);
+    return e;
+}
+
 int run_reduce(const float* pred, const float* gt, const uint8_t* mask, int B, int H, int W,
                const cadl_params& p, const Ws& ws, cudaStream_t st, const StepPlan& plan = StepPlan()) {
     uint32_t f = phase_a_flags(p);
@@ -647,7 +670,37 @@ int cadl_stack_reduce(const float* pred, const float* gt, const uint8_t* mask, i
     int rc = check_common(B, H, W, workspace, workspace_bytes);
     if (rc) return rc;
     Ws ws = make_ws(workspace, B, H, W);
-    return run_reduce(pred, gt, mask, B, H, W, *params, ws, (cudaStream_t)stream);
+    StepPlan plan;
+    if (params->pyramid_prepared) { plan = concurrent_plan(ws, B); plan.pyr_prelaunched = false; }   // (only the grid split matters here)
+    return run_reduce(pred, gt, mask, B, H, W, *params, ws, (cudaStream_t)stream, plan);
+}
+
+int cadl_stack_prepare(const float* pred, const float* gt, int B, int H, int W, const cadl_params* params,
+                       void* workspace, size_t workspace_bytes, cadl_stream_t stream) {
+    if (!params || !pred || !gt) return CADL_ERR_NULL;
+    int rc = check_common(B, H, W, workspace, workspace_bytes);
+    if (rc) return rc;
+    Ws ws = make_ws(workspace, B, H, W);
+    const cadl_params& p = *params;
+    // the conditions of the streaming path that can be known from pred/gt alone (stream_path_ok checks the rest)
+    const bool ok = (p.terms & CADL_TERM_GRAD) && ws.has_pyr() && !g_force_tile && !g_force_generic && p.num_scales == 4 &&
+                    (W % 4 == 0) && aligned(pred, 16) && aligned(gt, 16) && p.eps_grad > 0.f && p.eps_grad <= 1000.f &&
+                    (!(p.terms & CADL_TERM_SI) || p.eps_si == p.eps_grad);
+    if (!ok) return CADL_ERR_UNSUPPORTED;
+    AuxStream* aux = aux_for_current_device();
+    if (!aux) return CADL_ERR_UNSUPPORTED;
+    PhaseBArgs a{};
+    a.pred = pred; a.gt = gt; a.B = B; a.H = H; a.W = W;
+    a.global_B = p.global_B > 0 ? p.global_B : B;
+    a.w_grad = p.w_grad; a.eps_grad = p.eps_grad; a.upstream = p.upstream;
+    a.b_part = ws.b_part();
+    for (int s = 0; s < 4; ++s) {
+        const int Hs = H >> s, Ws_ = W >> s;
+        const double nx = (double)a.global_B * Hs * (Ws_ - 1), ny = (double)a.global_B * (Hs - 1) * Ws_;
+        a.inv_nx[s] = nx > 0.0 ? (float)(1.0 / nx) : 0.f;
+        a.inv_ny[s] = ny > 0.0 ? (float)(1.0 / ny) : 0.f;
+    }
+    return cuda_rc(prelaunch_pyramid(a, ws, (cudaStream_t)stream, aux, concurrent_plan(ws, B)));
 }
 
 int cadl_stack_grad(const float* pred, const float* gt, const float* rgb, const float* K, const uint8_t* mask,
@@ -657,7 +710,17 @@ int cadl_stack_grad(const float* pred, const float* gt, const float* rgb, const 
     int rc = check_common(B, H, W, workspace, workspace_bytes);
     if (rc) return rc;
     Ws ws = make_ws(workspace, B, H, W);
-    return run_grad(pred, gt, rgb, K, mask, B, H, W, *params, grad_pred, results, ws, (cudaStream_t)stream);
+    StepPlan plan;
+    if (params->pyramid_prepared) {
+        AuxStream* aux = aux_for_current_device();
+        if (!aux) return CADL_ERR_UNSUPPORTED;
+        plan = concurrent_plan(ws, B);
+        cudaError_t e = cudaStreamWaitEvent((cudaStream_t)stream, aux->join, 0);
+        if (e != cudaSuccess) return cuda_rc(e);
+        // (if the gradient part then takes another kernel -- e.g. an unaligned gradient buffer -- the prepared
+        //  pyramid is simply not used)
+    }
+    return run_grad(pred, gt, rgb, K, mask, B, H, W, *params, grad_pred, results, ws, (cudaStream_t)stream, plan);
 }
 
 int cadl_stack_fwd_bwd(const float* pred, const float* gt, const float* rgb, const float* K, const uint8_t* mask,
@@ -678,19 +741,9 @@ int cadl_stack_fwd_bwd(const float* pred, const float* gt, const float* rgb, con
         bool nothing = false;
         if (fill_b_args(a, pred, gt, rgb, K, mask, B, H, W, *params, grad_pred, results, ws, &nothing) == CADL_OK && !nothing &&
             stream_path_ok(a, *params, ws) && (aux = aux_for_current_device()) != nullptr) {
-            const int sms = num_sms_cached();
-            // two pyramid CTAs per SM, the rest of the 4-CTA wave for phase A (measured at config 3, us/step:
-            // 222 CTAs 207.4, 260 202.0, 280 195.2, 296 196.2, 330 198.9, 370 214.8; in line on one stream 208.7)
-            const int pyr_ctas = 2 * sms;
-            plan.pyr_grid = ws.L.pyr_blocks < pyr_ctas ? ws.L.pyr_blocks : pyr_ctas;
-            // phase A: 4 CTAs of 256 threads per SM; everything must fit ONE wave (more, shorter phase-A blocks
-            // starve the pyramid: 13 blocks per image 207.0 us/step, 18: 204.8, 36: 208.7 against 9: 196.5)
-            plan.a_blocks_per_img = (4 * sms - plan.pyr_grid) / B;
-            if (plan.a_blocks_per_img < 1) plan.a_blocks_per_img = 1;
-            cudaError_t e = cudaEventRecord(aux->fork, st);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(aux->s2, aux->fork, 0);
-            if (e == cudaSuccess) e = launch_pyramid(a, ws, aux->s2, plan.pyr_grid, false, !g_no_pdl);
-            if (e == cudaSuccess) e = cudaEventRecord(aux->join, aux->s2);
+            plan = concurrent_plan(ws, B);
+            plan.pyr_prelaunched = false;
+            cudaError_t e = prelaunch_pyramid(a, ws, st, aux, plan);
             if (e != cudaSuccess) return cuda_rc(e);
             plan.pyr_prelaunched = true;
         }

@@ -7,7 +7,9 @@ only coupling between ranks is the statistics vector phase A produces (counts an
                            do with the reference -- and no data-path collective exists;
   mode "global"            exact global-batch loss: all-reduce(sum) of the statistics vector between
                            phase A and phase B (cadl_stack_reduce / cadl_stack_grad), then the additive
-                           shares of the two stencil terms are summed for logging.
+                           shares of the two stencil terms are summed for logging.  cadl_stack_prepare first
+                           puts the pooled-pyramid kernels on an auxiliary stream, where they run beside
+                           phase A and the all-reduce instead of in front of the gradient pass.
 """
 from __future__ import annotations
 

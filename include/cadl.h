@@ -68,6 +68,9 @@ typedef struct cadl_params {
     float upstream;                         /* dL/dloss folded into the gradient (1.0 = loss.backward()) */
     /* exact-global-batch mode (SURVEY 8e mode B): this rank holds B of global_B images */
     int32_t global_B;                       /* 0 or B: single process */
+    /* split API only: cadl_stack_prepare was called for this step (same pred/gt/shape/params/workspace/stream, same
+     * host thread) and returned CADL_OK -- cadl_stack_reduce then shares the SMs with it and cadl_stack_grad joins it */
+    int32_t pyramid_prepared;
 } cadl_params;
 
 /* Everything the hot path returns, written on the device by the last block of the last kernel.
@@ -131,6 +134,15 @@ int cadl_stack_fwd_bwd(const float* pred, const float* gt, const float* rgb, con
                        const uint8_t* mask, int B, int H, int W, const cadl_params* params,
                        float* grad_pred, cadl_results* results, void* workspace,
                        size_t workspace_bytes, cadl_stream_t stream);
+
+/* Split API, optional first call of a step: start the pooled-pyramid kernels of the gradient-matching term (they
+ * need pred/gt and shape constants only) on an internal auxiliary stream forked from `stream`, so that they run
+ * beside cadl_stack_reduce and the caller's all-reduce instead of in front of the gradient pass.  Returns
+ * CADL_ERR_UNSUPPORTED when the streaming fast path does not apply (shape not a multiple of 8, unaligned pointers,
+ * num_scales != 4, no gradient-matching term ...): then leave params->pyramid_prepared at 0.  On CADL_OK set
+ * params->pyramid_prepared = 1 for the cadl_stack_reduce and cadl_stack_grad calls of THIS step. */
+int cadl_stack_prepare(const float* pred, const float* gt, int B, int H, int W, const cadl_params* params,
+                       void* workspace, size_t workspace_bytes, cadl_stream_t stream);
 
 /* The same computation split at its one global dependency: phase A reduces the
  * batch-global scalars into a vector of `cadl_stats_count()` doubles at

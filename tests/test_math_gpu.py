@@ -140,3 +140,28 @@ def test_step_captures_into_a_cuda_graph(pkg):
     torch.cuda.synchronize()
     assert torch.equal(grad, g_eager)
     assert pkg.results_dict(ws.read_results()) == r_eager
+
+
+@pytest.mark.parametrize("shape", [(4, 96, 256), (2, 37, 53)])
+def test_split_api_with_prepared_pyramid(pkg, shape):
+    """cadl_stack_prepare + cadl_stack_reduce + cadl_stack_grad (the global-batch flow) equals the fused call bit for
+    bit; on a shape the streaming path does not take, prepare reports "unsupported" and the flow is unchanged."""
+    B, H, W = shape
+    d = torch.device("cuda:0")
+    b = pkg.synth.make_batch(B, H, W, seed=B * H, device=d)
+    p = pkg.default_params(metrics=3)
+    w1 = pkg.stack_fwd_bwd(b["pred"], b["gt"], b["rgb"], b["K"], None, params=p)
+    r1, g1 = pkg.results_dict(w1.read_results()), w1.grad.clone()
+    ws = pkg.Workspace(B, H, W, d)
+    grad = torch.empty_like(b["pred"])
+    p2 = pkg.default_params(metrics=3)
+    prepared = pkg.stack_prepare(b["pred"], b["gt"], p2, ws)
+    assert prepared == (H % 8 == 0 and W % 8 == 0) and p2.pyramid_prepared == int(prepared)
+    pkg.stack_reduce(b["pred"], b["gt"], None, p2, ws)
+    pkg.stack_grad(b["pred"], b["gt"], b["rgb"], b["K"], None, p2, grad, ws)
+    torch.cuda.synchronize()
+    r2 = pkg.results_dict(ws.read_results())
+    assert torch.equal(grad, g1)
+    for k in ("loss_total", "si_loss", "grad_loss", "smooth_loss", "reproj_loss"):
+        assert rel_err(r2[k], r1[k]) == 0.0, (k, r2[k], r1[k])
+    assert r2["eval_counts"] == r1["eval_counts"] and r2["train_counts"] == r1["train_counts"]

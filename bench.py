@@ -234,6 +234,7 @@ def main():
     with ClockSampler(local_rank) as clk:
         ms_step = timed(step, args.steps, args.warmup)
         # per-phase durations for the roofline of the dominant kernel (same launches, timed apart)
+        params.pyramid_prepared = 0          # the phase timings below launch everything in line
         ms_a = timed(lambda: pkg.stack_reduce(pred, gt, None, params, ws), args.steps, 3)
         ms_b = timed(lambda: pkg.stack_grad(pred, gt, rgb, K, None, params, grad, ws), args.steps, 3)
         # every launch of the step between its own pair of CUDA events (this mode synchronises after each step and

@@ -160,6 +160,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="mode global: statistics exchange by our peer-memory kernel over NVLink (default) or NCCL all-reduce")
     ap.add_argument("--mode", default="local", choices=["local", "global"],
                     help="multi-GPU: local = each rank evaluates its own batch (DDP semantics, no exchange); "
                          "global = exact global-batch loss, one all-reduce of the 32-double statistics vector")
@@ -209,11 +211,26 @@ def main():
     if args.mode == "global" and world > 1:
         params.global_B = B_PER_GPU * world
 
+    p2p = None
+    if args.mode == "global" and world > 1 and args.exchange == "p2p":
+        p2p = pkg.multi.P2PStatsExchange(pkg, dev)
+        # one-off check: the peer-memory exchange and the NCCL all-reduce give the same sums
+        pkg.stack_reduce(pred, gt, None, params, ws)
+        ref_stats = ws.stats_view().clone()
+        dist.all_reduce(ref_stats)
+        p2p.exchange(ws)
+        torch.cuda.synchronize()
+        rel = float(((ws.stats_view() - ref_stats).abs() / ref_stats.abs().clamp_min(1e-300)).max())
+        assert not p2p.timed_out() and rel <= 1e-12, f"p2p exchange disagrees with NCCL: {rel}"
+
     def step():
         if args.mode == "global" and world > 1:
-            pkg.stack_prepare(pred, gt, params, ws)          # pyramid kernels beside phase A and the all-reduce
+            pkg.stack_prepare(pred, gt, params, ws)          # pyramid kernels beside phase A and the exchange
             pkg.stack_reduce(pred, gt, None, params, ws)
-            dist.all_reduce(ws.stats_view())                 # 32 doubles over NVLink (NCCL), stream-ordered
+            if p2p is not None:
+                p2p.exchange(ws)                             # 32 doubles pushed into every rank's inbox over NVLink
+            else:
+                dist.all_reduce(ws.stats_view())             # the same through NCCL, stream-ordered
             pkg.stack_grad(pred, gt, rgb, K, None, params, grad, ws)
         else:
             pkg.stack_fwd_bwd(pred, gt, rgb, K, None, params=params, grad=grad, ws=ws)
@@ -334,6 +351,7 @@ def main():
             "config": {"workload": "config3: full loss stack (SI+grad+smooth+reproj) fwd+bwd + DepthMetrics + "
                                    "computeDepthMetrics, B=32/GPU 480x640",
                        "pixels_per_step_per_gpu": P, "multi_gpu_mode": args.mode,
+                       "stats_exchange": (args.exchange if (args.mode == "global" and world > 1) else "none"),
                        "l2": "inputs+gradient 275 MB per step > 126 MB L2 (no flush needed)",
                        "seed": "1234 + rank"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,

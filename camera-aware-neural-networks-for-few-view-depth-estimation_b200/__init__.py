@@ -67,6 +67,7 @@ ABI_SYMBOLS = (
     "cadl_batch_prep", "cadl_clip_workspace_bytes", "cadl_clip_grad_norm", "cadl_debug_set_trace",
     "cadl_debug_kernel_times",
     "cadl_batch_augment", "cadl_accumulate", "cadl_stack_prepare",
+    "cadl_p2p_inbox_bytes", "cadl_p2p_alloc", "cadl_p2p_open", "cadl_p2p_close", "cadl_stats_exchange", "cadl_p2p_error",
 )
 
 _lib = None
@@ -415,6 +416,7 @@ class GradClipper:
 
 from .harness import StepHarness, StepCfg  # noqa: E402
 from . import synth  # noqa: E402
+from . import multi  # noqa: E402
 from .rays_io import save_ray_directions, load_ray_directions  # noqa: E402
 
 

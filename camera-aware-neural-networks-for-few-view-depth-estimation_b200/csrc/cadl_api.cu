@@ -864,6 +864,61 @@ int cadl_batch_augment(const float* rgb_in, const float* depth_in, const float* 
     return cuda_rc(launch_batch_prep(a, (cudaStream_t)stream));
 }
 
+size_t cadl_p2p_inbox_bytes(int world) {
+    if (world < 1 || world > kP2PMaxWorld) return 0;
+    return align_up(sizeof(double) * 2 * (size_t)world * kP2PSlotDoubles + sizeof(int) * 4, 256);
+}
+
+int cadl_p2p_alloc(int world, void** inbox_dev, unsigned char handle_out[64]) {
+    if (!inbox_dev || !handle_out) return CADL_ERR_NULL;
+    const size_t bytes = cadl_p2p_inbox_bytes(world);
+    if (!bytes) return CADL_ERR_SHAPE;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { if (p) cudaFree(p); return cuda_rc(e); }
+    memcpy(handle_out, &h, 64);
+    *inbox_dev = p;
+    return CADL_OK;
+}
+
+int cadl_p2p_open(const unsigned char handle[64], void** inbox_dev) {
+    if (!handle || !inbox_dev) return CADL_ERR_NULL;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    return cuda_rc(cudaIpcOpenMemHandle(inbox_dev, h, cudaIpcMemLazyEnablePeerAccess));
+}
+
+int cadl_p2p_close(void* inbox_dev, int own) {
+    if (!inbox_dev) return CADL_ERR_NULL;
+    return cuda_rc(own ? cudaFree(inbox_dev) : cudaIpcCloseMemHandle(inbox_dev));
+}
+
+int cadl_stats_exchange(void* workspace, void* const* inboxes_host, int rank, int world, unsigned long long epoch,
+                        cadl_stream_t stream) {
+    if (!workspace || !inboxes_host) return CADL_ERR_NULL;
+    if (world < 1 || world > kP2PMaxWorld || rank < 0 || rank >= world || epoch == 0) return CADL_ERR_SHAPE;
+    P2PArgs a{};
+    a.stats = reinterpret_cast<double*>(static_cast<char*>(workspace) + cadl_stats_offset());
+    for (int r = 0; r < world; ++r) {
+        if (!inboxes_host[r]) return CADL_ERR_NULL;
+        a.inbox[r] = static_cast<double*>(inboxes_host[r]);
+    }
+    a.rank = rank; a.world = world; a.epoch = epoch;
+    a.error = reinterpret_cast<int*>(a.inbox[rank] + 2 * (size_t)world * kP2PSlotDoubles);
+    stats_exchange_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(a);
+    return cuda_rc(cudaGetLastError());
+}
+
+int cadl_p2p_error(const void* own_inbox_dev, int world, int* error_host) {
+    if (!own_inbox_dev || !error_host) return CADL_ERR_NULL;
+    const char* p = static_cast<const char*>(own_inbox_dev) + sizeof(double) * 2 * (size_t)world * kP2PSlotDoubles;
+    return cuda_rc(cudaMemcpy(error_host, p, sizeof(int), cudaMemcpyDeviceToHost));
+}
+
 int cadl_accumulate(const float* values_dev, int n, double weight, double* acc_dev, cadl_stream_t stream) {
     if (!values_dev || !acc_dev) return CADL_ERR_NULL;
     if (n < 1) return CADL_ERR_SHAPE;

@@ -201,4 +201,60 @@ __global__ void __launch_bounds__(256) gradscale_kernel(const ClipArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Exact global-batch mode (SURVEY 8e mode B) without a collective library call: the 32-double statistics vector is
+// exchanged by ONE small kernel per rank over NVLink peer memory.  Every rank owns an "inbox" (cudaMalloc + CUDA IPC,
+// mapped by all peers): 2 parities x world slots of {32 doubles, epoch flag}.  The kernel
+//   1. pushes this rank's vector into slot [epoch & 1][rank] of every peer's inbox (plain stores over NVLink),
+//      fences (system scope) and then publishes the epoch flag of each slot;
+//   2. waits until all `world` flags of its OWN inbox carry this epoch;
+//   3. sums the slots in rank order (fixed order: every rank computes bit-identical sums) into its statistics vector.
+// Two parities suffice: nobody can start epoch e+1 before it has read epoch e, and epoch e+2 needs everybody's e+1.
+// The wait is bounded (~2 s of globaltimer): on timeout the kernel flags an error instead of hanging the GPU.
+// ------------------------------------------------------------------------------------------------
+constexpr int kP2PSlotDoubles = ST_COUNT + 2;     // 32 values, flag, pad
+constexpr int kP2PMaxWorld = 16;
+
+struct P2PArgs {
+    double* stats;                      // this rank's statistics vector (in/out)
+    double* inbox[kP2PMaxWorld];        // inbox[r]: rank r's inbox as mapped in THIS process (inbox[rank] = own)
+    int rank, world;
+    unsigned long long epoch;           // > 0, the same on every rank, incremented per exchange
+    int* error;                         // set to 1 on timeout
+};
+
+__global__ void __launch_bounds__(64) stats_exchange_kernel(const P2PArgs a) {
+    const int t = threadIdx.x;
+    const size_t slot = ((size_t)(a.epoch & 1ull) * a.world + a.rank) * kP2PSlotDoubles;
+    if (t < ST_COUNT) {
+        const double v = a.stats[t];
+        for (int p = 0; p < a.world; ++p) reinterpret_cast<volatile double*>(a.inbox[p] + slot)[t] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < a.world) {
+        unsigned long long* flag = reinterpret_cast<unsigned long long*>(a.inbox[t] + slot + ST_COUNT);
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(flag), "l"(a.epoch) : "memory");
+        // wait for rank t's contribution in the own inbox
+        const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(
+            a.inbox[a.rank] + ((size_t)(a.epoch & 1ull) * a.world + t) * kP2PSlotDoubles + ST_COUNT);
+        unsigned long long t0, now, seen = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+            if (seen == a.epoch) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > 2000000000ull) { *a.error = 1; break; }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    if (t < ST_COUNT) {
+        double sum = 0.0;
+        for (int r = 0; r < a.world; ++r)
+            sum += reinterpret_cast<const volatile double*>(a.inbox[a.rank] + ((size_t)(a.epoch & 1ull) * a.world + r) * kP2PSlotDoubles)[t];
+        a.stats[t] = sum;
+    }
+}
+
 }  // namespace cadl

@@ -38,6 +38,72 @@ def exchange_stats(stats: torch.Tensor, group: Optional[dist.ProcessGroup] = Non
     return stats
 
 
+class P2PStatsExchange:
+    """Mode "global" without a collective call: one small kernel per rank pushes the statistics vector into every
+    rank's inbox over NVLink peer memory and sums the inboxes in rank order (include/cadl.h: cadl_stats_exchange).
+    Setup (once): every rank allocates its inbox and the 64-byte CUDA IPC handles are all-gathered through
+    torch.distributed; per step: ``exchange(ws)`` between stack_reduce and stack_grad, on the current stream."""
+
+    def __init__(self, pkg, device: torch.device, group: Optional[dist.ProcessGroup] = None):
+        import ctypes as C
+        self.pkg, self.C, self.L = pkg, C, pkg.lib()
+        self.device = device
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.epoch = 0
+        L = self.L
+        L.cadl_p2p_alloc.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_char_p]
+        L.cadl_p2p_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.cadl_p2p_close.argtypes = [C.c_void_p, C.c_int]
+        L.cadl_stats_exchange.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_ulonglong, C.c_void_p]
+        L.cadl_p2p_error.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        with torch.cuda.device(device):
+            own = C.c_void_p()
+            handle = C.create_string_buffer(64)
+            pkg._check(L.cadl_p2p_alloc(self.world, C.byref(own), handle), "cadl_p2p_alloc")
+            self.own = own
+            mine = torch.tensor(list(handle.raw), dtype=torch.uint8)
+            if self.world > 1:
+                gathered = [torch.zeros(64, dtype=torch.uint8, device=device) for _ in range(self.world)]
+                dist.all_gather(gathered, mine.to(device), group=group)
+                handles = [bytes(g.cpu().tolist()) for g in gathered]
+            else:
+                handles = [bytes(mine.tolist())]
+            self.ptrs = (C.c_void_p * self.world)()
+            for r in range(self.world):
+                if r == self.rank:
+                    self.ptrs[r] = own.value
+                else:
+                    q = C.c_void_p()
+                    pkg._check(L.cadl_p2p_open(handles[r], C.byref(q)), "cadl_p2p_open")
+                    self.ptrs[r] = q.value
+            torch.cuda.synchronize(device)
+        if self.world > 1:
+            dist.barrier(group=group)          # every inbox is mapped everywhere before the first push
+
+    def exchange(self, ws) -> None:
+        """Sum the statistics vectors of all ranks in place (stream-ordered, no host sync)."""
+        self.epoch += 1
+        with torch.cuda.device(self.device):
+            rc = self.L.cadl_stats_exchange(self.pkg._ptr(ws.buf), self.ptrs, self.rank, self.world, self.epoch,
+                                            self.C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        self.pkg._check(rc, "cadl_stats_exchange")
+
+    def timed_out(self) -> bool:
+        e = self.C.c_int(0)
+        with torch.cuda.device(self.device):
+            self.pkg._check(self.L.cadl_p2p_error(self.own, self.world, self.C.byref(e)), "cadl_p2p_error")
+        return e.value != 0
+
+    def close(self) -> None:
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for r in range(self.world):
+                if self.ptrs[r]:
+                    self.L.cadl_p2p_close(self.ptrs[r], int(r == self.rank))
+                    self.ptrs[r] = None
+
+
 def si_from_stats(stats: torch.Tensor, lam: float = 0.5) -> float:
     """ScaleInvariantLoss from (n, sum d, sum d^2): depth_loss.h:58-63 (zero when n == 0, :53-55)."""
     n, S, Q = float(stats[ST_SI_N]), float(stats[ST_SI_S]), float(stats[ST_SI_Q])

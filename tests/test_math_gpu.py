@@ -165,3 +165,24 @@ def test_split_api_with_prepared_pyramid(pkg, shape):
     for k in ("loss_total", "si_loss", "grad_loss", "smooth_loss", "reproj_loss"):
         assert rel_err(r2[k], r1[k]) == 0.0, (k, r2[k], r1[k])
     assert r2["eval_counts"] == r1["eval_counts"] and r2["train_counts"] == r1["train_counts"]
+
+
+def test_p2p_stats_exchange_single_rank(pkg):
+    """cadl_stats_exchange with world = 1 (own inbox only): the statistics vector comes back unchanged, for both
+    epoch parities and repeatedly; no timeout is flagged.  (world > 1 is checked against NCCL by bench.py --mode global.)"""
+    d = torch.device("cuda:0")
+    b = pkg.synth.make_batch(2, 48, 64, seed=9, device=d)
+    ws = pkg.Workspace(2, 48, 64, d)
+    p = pkg.default_params(metrics=3)
+    pkg.stack_reduce(b["pred"], b["gt"], None, p, ws)
+    torch.cuda.synchronize()
+    before = ws.stats_view().clone()
+    x = pkg.multi.P2PStatsExchange(pkg, d)
+    try:
+        for _ in range(5):
+            x.exchange(ws)
+        torch.cuda.synchronize()
+        assert torch.equal(ws.stats_view(), before)
+        assert not x.timed_out()
+    finally:
+        x.close()

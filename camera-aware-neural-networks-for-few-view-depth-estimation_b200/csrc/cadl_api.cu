@@ -378,12 +378,13 @@ cudaError_t launch_stream(PhaseBArgs& a, const Ws& ws, cudaStream_t st, bool* of
 
 template <int F>
 cudaError_t launch_point_fast(PhaseBArgs& a, cudaStream_t st) {
-    // (blocks per image, B) with ~8 CTAs per SM in total; a_rows = grid size (partial rows, ticket)
-    // whole rows per warp, as even as possible: rows_per_warp = round(H*B / (8 warps * ~8 CTAs * 148 SMs))
+    // (blocks per image, B): ONE resident wave -- the kernel is capped at 64 registers, 4 CTAs of 256 threads per SM
+    // (the earlier sizing assumed 8 per SM and ran 1.6 waves); its warps deal the image's 128-pixel row segments
+    // round-robin.  b_rows = grid size (partial rows, ticket).
     const int wpb = kThreadsB / 32;
-    int rpw = (int)(((long long)a.H * a.B + (148LL * 8 * wpb) / 2) / (148LL * 8 * wpb));
-    if (rpw < 1) rpw = 1;
-    int bpi = (a.H + wpb * rpw - 1) / (wpb * rpw);
+    int bpi = (4 * num_sms_cached()) / a.B;
+    const int max_bpi = (a.H * ((a.W + 127) / 128) + wpb - 1) / wpb;        // at least one segment per warp
+    if (bpi > max_bpi) bpi = max_bpi;
     while (bpi > 1 && bpi * a.B > kPointBlocks) --bpi;
     if (bpi < 1) bpi = 1;
     dim3 grid(bpi, a.B);

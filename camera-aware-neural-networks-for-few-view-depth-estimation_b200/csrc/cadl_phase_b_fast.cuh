@@ -731,30 +731,44 @@ __global__ void __launch_bounds__(kThreadsB, 4) phase_b_point_fast_kernel(const 
         rfx = __frcp_rn(fxe); rfy = __frcp_rn(fye);
         mk_ok = markstein_safe(fxe) && markstein_safe(fye);
     }
+    // Work items = 128-pixel row segments of this image, dealt round-robin to the warps of the image's CTAs (whole
+    // rows per warp left some warps with 4 rows and others with 3 at config 2).  NB items per batch: all loads of
+    // a batch are issued before any arithmetic.
     const int wstride = gridDim.x * (kThreadsB / 32);
-    for (int y = blockIdx.x * (kThreadsB / 32) + warp; y < H; y += wstride) {
-      const int row = b * H + y;
-      const float ayv = RP ? (float)y - cyv : 0.f;
-      const float yh = ayv * rfy;                         // d pY / d p, tolerance path
-      // NB row segments (128 px each) per batch: all loads of a batch are issued before any arithmetic
-      constexpr int NB = 3;
-      for (int seg0 = 0; seg0 < segs; seg0 += NB) {
+    const int items = H * segs;
+    constexpr int NB = 3;
+    // (row, segment) of an item advance by a fixed (dq, dr) per stride: no integer division in the loop
+    const int dq = wstride / segs, dr = wstride - dq * segs;
+    int i0 = blockIdx.x * (kThreadsB / 32) + warp;
+    int y0 = i0 / segs, s0 = i0 - y0 * segs;
+    for (; i0 < items; i0 += NB * wstride) {
+      {
         float4 p4[NB], g4[NB];
         uchar4 u4[NB];
+        int ys[NB], xs[NB];
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
-          const int x = ((seg0 + j) << 7) + 4 * lane;
+          ys[j] = y0;
+          xs[j] = (s0 << 7) + 4 * lane;
+          const bool on = (i0 + j * wstride < items) && xs[j] < W;
+          if (!on) xs[j] = -1;
           p4[j] = make_float4(1.f, 1.f, 1.f, 1.f); g4[j] = make_float4(0.f, 0.f, 0.f, 0.f); u4[j] = make_uchar4(0, 0, 0, 0);
-          if (seg0 + j < segs && x < W) {
-            p4[j] = __ldg(reinterpret_cast<const float4*>(a.pred + row * W + x));
-            g4[j] = __ldg(reinterpret_cast<const float4*>(a.gt + row * W + x));
-            if constexpr (HAS_MASK) u4[j] = __ldg(reinterpret_cast<const uchar4*>(a.mask + row * W + x));
+          if (on) {
+            const int o = (b * H + y0) * W + xs[j];
+            p4[j] = __ldg(reinterpret_cast<const float4*>(a.pred + o));
+            g4[j] = __ldg(reinterpret_cast<const float4*>(a.gt + o));
+            if constexpr (HAS_MASK) u4[j] = __ldg(reinterpret_cast<const uchar4*>(a.mask + o));
           }
+          y0 += dq; s0 += dr;
+          if (s0 >= segs) { s0 -= segs; ++y0; }
         }
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
-          const int x = ((seg0 + j) << 7) + 4 * lane;
-          if (!(seg0 + j < segs && x < W)) continue;
+          const int y = ys[j], x = xs[j];
+          if (x < 0) continue;
+          const int row = b * H + y;
+          const float ayv = RP ? (float)y - cyv : 0.f;
+          const float yh = ayv * rfy;                         // d pY / d p, tolerance path
           const int off = row * W + x;
           const bool um[4] = {u4[j].x != 0, u4[j].y != 0, u4[j].z != 0, u4[j].w != 0};
           const float p[4] = {p4[j].x, p4[j].y, p4[j].z, p4[j].w}, g[4] = {g4[j].x, g4[j].y, g4[j].z, g4[j].w};

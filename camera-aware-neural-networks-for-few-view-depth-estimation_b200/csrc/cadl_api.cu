@@ -85,6 +85,7 @@ struct Ws {
 
 int g_force_generic = 0;
 int g_force_tile = 0;
+int g_no_coop = 0;          // bit 6: reprojection alone keeps the separate count kernel (no cooperative launch)
 int g_no_overlap = 0;       // bit 5: pooled-pyramid kernels in line on the caller's stream instead of beside phase A
 int g_no_pdl = 0;           // bit 4: plain stream-ordered launches (no programmatic dependent launch)
 // cadl_debug_kernel_times: CUDA events between the launches of one cadl_stack_fwd_bwd call (debug / profiling aid)
@@ -394,6 +395,32 @@ cudaError_t launch_point_fast(PhaseBArgs& a, cudaStream_t st) {
     return launch_pdl(phase_b_point_fast_kernel<F, false>, grid, dim3(kThreadsB), st, pdl, a);
 }
 
+// Reprojection alone, no metrics: count + gradient in ONE cooperative launch (phase_b_point_fast_kernel<.., COUNT>).
+// Returns cudaErrorNotSupported when the grid cannot be co-resident, so the caller takes the two-launch path.
+cudaError_t launch_point_count(PhaseBArgs& a, cudaStream_t st) {
+    static int coop = -1;
+    if (coop < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    }
+    if (!coop) return cudaErrorNotSupported;
+    const int wpb = kThreadsB / 32;
+    int bpi = (4 * num_sms_cached()) / a.B;
+    const int max_bpi = (a.H * ((a.W + 127) / 128) + wpb - 1) / wpb;
+    if (bpi > max_bpi) bpi = max_bpi;
+    if (bpi < 1) return cudaErrorNotSupported;                    // more images than resident CTAs
+    void* fn = a.mask ? (void*)phase_b_point_fast_kernel<FB_RP, true, true> : (void*)phase_b_point_fast_kernel<FB_RP, false, true>;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreadsB, 0);
+    if (e != cudaSuccess) return e;
+    if ((long long)bpi * a.B > (long long)per_sm * num_sms_cached()) return cudaErrorNotSupported;
+    dim3 grid(bpi, a.B);
+    a.b_rows = bpi * a.B;
+    void* args[] = {(void*)&a};
+    return cudaLaunchCooperativeKernel(fn, grid, dim3(kThreadsB), args, 0, st);
+}
+
 template <int F>
 cudaError_t launch_point(const PhaseBArgs& a, cudaStream_t st) {
     phase_b_point_kernel<F><<<a.b_rows, kThreadsB, 0, st>>>(a);
@@ -621,6 +648,7 @@ void cadl_debug_force_generic(int on) {
     g_force_tile = (on >> 3) & 1;
     g_no_pdl = (on >> 4) & 1;
     g_no_overlap = (on >> 5) & 1;
+    g_no_coop = (on >> 6) & 1;
     g_use_ws = (on >> 2) & 1;
 }
 size_t cadl_sizeof_params(void) { return sizeof(cadl_params); }
@@ -747,6 +775,19 @@ int cadl_stack_fwd_bwd(const float* pred, const float* gt, const float* rgb, con
             cudaError_t e = prelaunch_pyramid(a, ws, st, aux, plan);
             if (e != cudaSuccess) return cuda_rc(e);
             plan.pyr_prelaunched = true;
+        }
+    }
+    // Reprojection alone, no metrics (BASELINE config 2): the gradient kernel counts the valid pixels itself
+    if ((params->terms & CADL_TERM_ALL) == CADL_TERM_REPROJ && params->metrics == 0 && !g_force_generic && !g_no_coop &&
+        !g_kt.on && results) {
+        PhaseBArgs a;
+        bool nothing = false;
+        if (fill_b_args(a, pred, gt, rgb, K, mask, B, H, W, *params, grad_pred, results, ws, &nothing) == CADL_OK && !nothing &&
+            a.vec_ok) {
+            cudaError_t e = launch_point_count(a, st);
+            if (e == cudaSuccess) return CADL_OK;
+            if (e != cudaErrorNotSupported && e != cudaErrorCooperativeLaunchTooLarge) return cuda_rc(e);
+            cudaGetLastError();            // not co-resident on this device / this shape: two launches
         }
     }
     rc = run_reduce(pred, gt, mask, B, H, W, *params, ws, st, plan);

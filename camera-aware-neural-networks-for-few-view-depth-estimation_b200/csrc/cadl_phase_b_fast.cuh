@@ -19,6 +19,7 @@
 // overlaps the other's arithmetic.
 #pragma once
 #include <cuda.h>   // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
+#include <cooperative_groups.h>
 #include "cadl_common.cuh"
 #include "cadl_math.cuh"
 #include "cadl_phase_a.cuh"
@@ -695,21 +696,73 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
 // One warp per 128-pixel row segment, 2 segments in flight per warp; 12 B/px of HBM traffic.
 // Requires W % 4 == 0 and 16-byte aligned tensors (same dispatch condition as the tile fast path).
 // ================================================================================================
-template <int F, bool HAS_MASK>
+// COUNT (reprojection alone, cooperative launch): the kernel counts the valid pixels itself in a first sweep over gt
+// (the only statistic this term needs), meets at a grid-wide barrier, and then runs the gradient sweep -- no separate
+// phase-A launch, no reduce-kernel epilogue, no launch gap (~8 us of a 43 us step at config 2).
+template <int F, bool HAS_MASK, bool COUNT = false>
 __global__ void __launch_bounds__(kThreadsB, 4) phase_b_point_fast_kernel(const PhaseBArgs a) {
     __shared__ float s_f[kThreadsB / 32][BF_COUNT];
     __shared__ double s_d[8];
     __shared__ float s_c[4];
     __shared__ int s_last;
+    __shared__ unsigned s_cnt[kThreadsB / 32];
     constexpr bool SI = (F & FB_SI) != 0, RP = (F & FB_RP) != 0;
+    static_assert(!COUNT || F == FB_RP, "the in-kernel count exists for the reprojection term alone");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float up = a.upstream;
+    if constexpr (COUNT) {
+        const int segs = (a.W + 127) >> 7, items = a.H * segs, b = blockIdx.y;
+        const int wstride = gridDim.x * (kThreadsB / 32);
+        unsigned cnt = 0;
+        const int dq = wstride / segs, dr = wstride - dq * segs;
+        int it = blockIdx.x * (kThreadsB / 32) + warp;
+        int y = it / segs, sg = it - y * segs;
+        constexpr int NC = 6;                                   // loads in flight per lane
+        for (; it < items; it += NC * wstride) {
+            float4 g[NC];
+            uchar4 u[NC];
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+                const int x = (sg << 7) + 4 * lane;
+                g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                u[j] = make_uchar4(0, 0, 0, 0);
+                if (it + j * wstride < items && x < a.W) {
+                    const int o = (b * a.H + y) * a.W + x;
+                    if constexpr (HAS_MASK) u[j] = __ldg(reinterpret_cast<const uchar4*>(a.mask + o));
+                    else g[j] = __ldg(reinterpret_cast<const float4*>(a.gt + o));
+                }
+                y += dq; sg += dr;
+                if (sg >= segs) { sg -= segs; ++y; }
+            }
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+                if constexpr (HAS_MASK) cnt += (u[j].x != 0) + (u[j].y != 0) + (u[j].z != 0) + (u[j].w != 0);
+                else cnt += (g[j].x > a.eps_rp) + (g[j].y > a.eps_rp) + (g[j].z > a.eps_rp) + (g[j].w > a.eps_rp);   // depth_loss.h:318-320
+            }
+        }
+        cnt = warp_sum(cnt);
+        if (lane == 0) s_cnt[warp] = cnt;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned t = 0;
+            for (int w = 0; w < kThreadsB / 32; ++w) t += s_cnt[w];
+            atomicAdd(&a.hdr->icount[AI_RP_N], (unsigned long long)t);      // integer: order-free, exact
+        }
+        cooperative_groups::this_grid().sync();
+        if (tid == 0) {
+            const double nr = (double)*reinterpret_cast<volatile unsigned long long*>(&a.hdr->icount[AI_RP_N]);
+            if (blockIdx.x == 0 && blockIdx.y == 0) const_cast<double*>(a.stats)[ST_RP_N] = nr;   // what finalize_results reads
+            s_c[0] = 0.f; s_c[1] = 0.f;
+            s_c[2] = nr > 0.0 ? (float)(1.0 / nr) * a.w_rp * up : 0.f;
+        }
+    } else {
     pdl_wait();        // launched behind phase A with programmatic stream serialization: its statistics
     if (tid == 0) {
         const double n = a.stats[ST_SI_N], S = a.stats[ST_SI_S], nr = a.stats[ST_RP_N];
         s_c[0] = n > 0.0 ? (float)(2.0 / n) * a.w_si * up : 0.f;
         s_c[1] = n > 0.0 ? (float)(-2.0 * (double)a.lambda * S / (n * n)) * a.w_si * up : 0.f;
         s_c[2] = nr > 0.0 ? (float)(1.0 / nr) * a.w_rp * up : 0.f;
+    }
     }
     __syncthreads();
     const float c1 = s_c[0], c2 = s_c[1], rpn = s_c[2];
@@ -820,6 +873,7 @@ __global__ void __launch_bounds__(kThreadsB, 4) phase_b_point_fast_kernel(const 
       }
     }
     if (publish_partials(a, acc, blockIdx.y * gridDim.x + blockIdx.x, s_f, &s_last)) {
+        if (COUNT && tid == 0) a.hdr->icount[AI_RP_N] = 0ull;      // everybody has read it: leave the counter clean
         finalize_results(a, s_d);
         if (a.metrics) write_metric_results(a.stats, a.metrics, *a.results, tid);
     }

@@ -100,7 +100,8 @@ const char* cadl_error_string(int code);
  * aligned fast path; 8 = fast path as ONE tile kernel (cadl_phase_b_fast.cuh) instead of the streaming split
  * (cadl_phase_b_stream.cuh); together with 8: 2 = stage tiles with cp.async instead of TMA, 4 = warp-specialised
  * persistent tile kernel (cadl_phase_b_ws.cuh); 16 = no programmatic dependent launch; 32 = the pooled-pyramid
- * kernels in line on the caller's stream instead of beside phase A on the auxiliary stream.  All variants must
+ * kernels in line on the caller's stream instead of beside phase A on the auxiliary stream; 64 = reprojection alone
+ * with the separate count kernel instead of the single cooperative launch.  All variants must
  * produce the same values.  Process-global; not for production use. */
 void cadl_debug_force_generic(int on);
 /* Debug trace of the streaming phase-B kernel: while dev_buf is non-NULL every warp (global index < capacity_warps)

@@ -186,3 +186,29 @@ def test_p2p_stats_exchange_single_rank(pkg):
         assert not x.timed_out()
     finally:
         x.close()
+
+
+@pytest.mark.parametrize("shape,masked", [((4, 96, 256), False), ((3, 40, 200), True), ((2, 37, 52), False), ((700, 8, 8), False)])
+def test_reprojection_alone_cooperative_count(pkg, shape, masked):
+    """BASELINE config 2 path: the single cooperative launch (count + gradient) equals the two-launch form bit for
+    bit (mode 64), including shapes where the cooperative form does not apply and the call falls back."""
+    B, H, W = shape
+    d = torch.device("cuda:0")
+    b = pkg.synth.make_batch(B, H, W, seed=H + W, device=d)
+    mask = (torch.rand(B, 1, H, W, device=d) < 0.7) if masked else None
+    out = {}
+    for mode in (0, 64):
+        pkg.force_generic(mode)
+        try:
+            ws = pkg.stack_fwd_bwd(b["pred"], b["gt"], None, b["K"], mask,
+                                   params=pkg.default_params(terms=pkg.TERM_REPROJ, w_reproj=1.0))
+            torch.cuda.synchronize()
+            out[mode] = (pkg.results_dict(ws.read_results()), ws.grad.clone())
+        finally:
+            pkg.force_generic(0)
+    assert torch.equal(out[0][1], out[64][1])
+    assert out[0][0]["reproj_loss"] == out[64][0]["reproj_loss"] and out[0][0]["n_reproj"] == out[64][0]["n_reproj"]
+    # and a second call right after (the kernel leaves its counter clean)
+    ws = pkg.stack_fwd_bwd(b["pred"], b["gt"], None, b["K"], mask, params=pkg.default_params(terms=pkg.TERM_REPROJ, w_reproj=1.0))
+    torch.cuda.synchronize()
+    assert torch.equal(ws.grad, out[0][1])

@@ -302,9 +302,7 @@ AuxStream* aux_for_current_device() {
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
     AuxStream& x = g_aux[dev];
     if (x.dev != dev) {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);      // hi = numerically lowest = highest priority
-        if (cudaStreamCreateWithPriority(&x.s2, cudaStreamNonBlocking, getenv("CADL_AUX_PRIO") ? hi : 0) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithFlags(&x.s2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         x.dev = dev;
@@ -440,7 +438,6 @@ StepPlan concurrent_plan(const Ws& ws, int B) {
     plan.pyr_grid = ws.L.pyr_blocks < pyr_ctas ? ws.L.pyr_blocks : pyr_ctas;
     plan.a_blocks_per_img = (4 * sms - plan.pyr_grid) / B;       // phase A: 4 CTAs of 256 threads per SM
     if (plan.a_blocks_per_img < 1) plan.a_blocks_per_img = 1;
-    { const char* ev = getenv("CADL_A_BPI"); if (ev) plan.a_blocks_per_img = atoi(ev); }
     plan.pyr_prelaunched = true;
     return plan;
 }
@@ -464,7 +461,7 @@ int run_reduce(const float* pred, const float* gt, const uint8_t* mask, int B, i
     a.pred = pred; a.gt = gt; a.mask = mask;
     a.B = B; a.HW = H * W;
     a.blocks_per_img = ws.L.a_blocks_per_img;
-    if (plan.a_blocks_per_img > 0 && plan.a_blocks_per_img <= a.blocks_per_img) a.blocks_per_img = plan.a_blocks_per_img;
+    if (plan.a_blocks_per_img > 0 && plan.a_blocks_per_img < a.blocks_per_img) a.blocks_per_img = plan.a_blocks_per_img;
     a.vec_ok = ((H * W) % 4 == 0) && (!pred || aligned(pred, 16)) && (!gt || aligned(gt, 16)) &&
                (!mask || aligned(mask, 4));
     a.eps_si = p.eps_si; a.eps_rp = p.eps_reproj; a.min_d = p.min_depth; a.max_d = p.max_depth;

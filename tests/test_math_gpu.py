@@ -212,3 +212,48 @@ def test_reprojection_alone_cooperative_count(pkg, shape, masked):
     ws = pkg.stack_fwd_bwd(b["pred"], b["gt"], None, b["K"], mask, params=pkg.default_params(terms=pkg.TERM_REPROJ, w_reproj=1.0))
     torch.cuda.synchronize()
     assert torch.equal(ws.grad, out[0][1])
+
+
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_streaming_equals_generic_on_hostile_inputs(pkg, seed):
+    """Random aligned shapes with special values planted in pred/gt/rgb (0, negatives, the clamp bounds, values far
+    outside them, +inf, NaN, exact ties pred == gt): the streaming path and the generic kernel must agree pixel for
+    pixel -- NaN where the other has NaN, within rounding elsewhere -- and so must the losses."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    B = int(torch.randint(1, 5, (1,), generator=g))
+    H = 8 * int(torch.randint(1, 10, (1,), generator=g))
+    W = 8 * int(torch.randint(1, 42, (1,), generator=g))
+    d = torch.device("cuda:0")
+    b = pkg.synth.make_batch(B, H, W, seed=seed, device=d)
+    pred, gt, rgb = b["pred"].clone(), b["gt"].clone(), b["rgb"].clone()
+    n = pred.numel()
+    specials = [0.0, -1.0, 1e-6, 1e-7, 1000.0, 1e4, 0.25, 0.1, 10.0]
+    if seed % 2:
+        specials += [float("inf"), float("nan")]
+    for t in (pred, gt):
+        idx = torch.randint(0, n, (max(4, n // 50),), generator=g).to(d)
+        vals = torch.tensor(specials, device=d)[torch.randint(0, len(specials), (idx.numel(),), generator=g).to(d)]
+        t.view(-1)[idx] = vals
+    tie = torch.randint(0, n, (max(4, n // 20),), generator=g).to(d)
+    pred.view(-1)[tie] = gt.view(-1)[tie]                                  # exact ties: sign(0) = 0 paths
+    rgb.view(-1)[torch.randint(0, rgb.numel(), (8,), generator=g).to(d)] = 0.0
+    res = {}
+    for mode in (1, 0):
+        pkg.force_generic(mode)
+        try:
+            ws = pkg.stack_fwd_bwd(pred, gt, rgb, b["K"], None, params=pkg.default_params(metrics=3))
+            torch.cuda.synchronize()
+            res[mode] = (pkg.results_dict(ws.read_results()), ws.grad.clone())
+        finally:
+            pkg.force_generic(0)
+    (rg, gg), (rs, gs) = res[1], res[0]
+    assert torch.equal(torch.isnan(gg), torch.isnan(gs))
+    fin = torch.isfinite(gg) & torch.isfinite(gs)
+    assert torch.equal(torch.isinf(gg), torch.isinf(gs))
+    if fin.any():
+        scale = float(gg[fin].abs().max())
+        assert float((gg[fin] - gs[fin]).abs().max()) <= 4e-6 * max(scale, 1e-30)
+    for k in ("loss_total", "si_loss", "grad_loss", "smooth_loss", "reproj_loss"):
+        assert rel_err(rs[k], rg[k]) <= 4e-6, (k, rs[k], rg[k])
+    assert rs["eval_counts"] == rg["eval_counts"] and rs["train_counts"] == rg["train_counts"]
+    assert rs["n_si"] == rg["n_si"] and rs["n_reproj"] == rg["n_reproj"]

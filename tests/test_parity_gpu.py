@@ -132,6 +132,46 @@ def test_smooth_set_sign_zero(pkg, oracle, oracle_device):
     _compare_case(pkg, oracle, b["pred"], b["gt"], b["rgb"], b["K"], None, oracle_device, "smooth")
 
 
+def _plant(t, values, frac, g):
+    n = t.numel()
+    idx = torch.randint(0, n, (max(4, int(n * frac)),), generator=g)
+    t.view(-1)[idx] = torch.tensor(values)[torch.randint(0, len(values), (idx.numel(),), generator=g)]
+
+
+@pytest.mark.parametrize("shape", [(2, 48, 136), (3, 37, 53)])      # streaming path / generic kernel
+def test_hostile_finite_values_vs_oracle(pkg, oracle, shape):
+    """Zeros, negatives, the clamp bounds, values far outside them and exact ties pred == gt planted in pred / gt:
+    losses and gradients still match the op-for-op oracle on CUDA (clamp backward on the closed interval, sign(0) = 0,
+    masks computed before clamping)."""
+    B, H, W = shape
+    g = torch.Generator().manual_seed(H * W)
+    b = pkg.synth.make_batch(B, H, W, seed=21)
+    pred, gt = b["pred"].clone(), b["gt"].clone()
+    _plant(pred, [0.0, -1.0, 1e-6, 1e-7, 1000.0, 1e4, 0.25, 0.1, 10.0], 0.03, g)
+    _plant(gt, [0.0, -1.0, 1e-6, 1e-7, 1000.0, 1e4, 0.25, 0.1, 10.0], 0.03, g)
+    tie = torch.randint(0, pred.numel(), (pred.numel() // 10,), generator=g)
+    pred.view(-1)[tie] = gt.view(-1)[tie]
+    _compare_case(pkg, oracle, pred, gt, b["rgb"], b["K"], None, "cuda", f"hostile{shape}")
+
+
+@pytest.mark.parametrize("shape", [(2, 48, 136), (3, 37, 53)])
+def test_nan_in_pred_propagates_like_the_reference(pkg, oracle, shape):
+    """One NaN in pred: which losses become NaN and which gradient pixels are NaN must be what the reference's op chain
+    produces (torch::clamp and the masked means let it through)."""
+    B, H, W = shape
+    b = pkg.synth.make_batch(B, H, W, seed=3)
+    pred = b["pred"].clone()
+    pred[1, 0, H // 2, W // 3] = float("nan")
+    ref = _oracle_all(oracle, pred, b["gt"], b["rgb"], b["K"], None, "cuda")
+    r, g = _ours(pkg, pred, b["gt"], b["rgb"], b["K"], None, pkg.TERM_ALL)
+    for name, key in (("si", "si_loss"), ("grad", "grad_loss"), ("smooth", "smooth_loss"), ("reproj", "reproj_loss")):
+        assert np.isnan(r[key]) == np.isnan(ref[name][0]), (name, r[key], ref[name][0])
+        if not np.isnan(ref[name][0]):
+            assert rel_err(r[key], ref[name][0]) <= TOL, name
+    gr = ref["total"][1].cpu()
+    assert torch.equal(torch.isnan(g), torch.isnan(gr)), (int(torch.isnan(g).sum()), int(torch.isnan(gr).sum()))
+
+
 def test_user_mask_and_k33(pkg, oracle):
     b = pkg.synth.make_batch(2, 64, 96, seed=9)
     g = torch.Generator().manual_seed(5)

@@ -427,14 +427,16 @@ cudaError_t launch_point(const PhaseBArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-// Grid split when the pyramid kernels run beside phase A: two pyramid CTAs per SM, the rest of the 4-CTA wave for
-// phase A (measured at config 3, us/step: 222 pyramid CTAs 207.4, 260 202.0, 280 195.2, 296 196.2, 330 198.9,
-// 370 214.8; in line on one stream 208.7).  Everything must fit ONE wave: more, shorter phase-A blocks starve the
-// pyramid (13 blocks per image 207.0 us/step, 18: 204.8, 36: 208.7 against 9: 196.5).
-StepPlan concurrent_plan(const Ws& ws, int B) {
+// Grid split when the pyramid kernels run beside phase A, in CTAs of 256 threads out of the 4 per SM that fit.
+// Phase A with the metric variants is the longer of the two: 2 pyramid CTAs per SM, the rest for phase A (config 3,
+// us/step: 222 pyramid CTAs 207.4, 260 202.0, 280 195.2, 296 196.2, 330 198.9, 370 214.8; in line 208.7).  Without
+// metrics (the trainers' step) phase A is short and the pyramid gets 3 per SM (296: 177.1, 370: 169.3, 444: 166.1,
+// 518: 189.9; in line 174.8).  Everything must fit ONE wave: more, shorter phase-A blocks starve the pyramid (13
+// blocks per image 207.0 us/step, 18: 204.8, 36: 208.7 against 9: 196.5).
+StepPlan concurrent_plan(const Ws& ws, int B, bool metrics) {
     StepPlan plan;
     const int sms = num_sms_cached();
-    const int pyr_ctas = 2 * sms;
+    const int pyr_ctas = (metrics ? 2 : 3) * sms;
     plan.pyr_grid = ws.L.pyr_blocks < pyr_ctas ? ws.L.pyr_blocks : pyr_ctas;
     plan.a_blocks_per_img = (4 * sms - plan.pyr_grid) / B;       // phase A: 4 CTAs of 256 threads per SM
     if (plan.a_blocks_per_img < 1) plan.a_blocks_per_img = 1;
@@ -700,7 +702,7 @@ int cadl_stack_reduce(const float* pred, const float* gt, const uint8_t* mask, i
     if (rc) return rc;
     Ws ws = make_ws(workspace, B, H, W);
     StepPlan plan;
-    if (params->pyramid_prepared) { plan = concurrent_plan(ws, B); plan.pyr_prelaunched = false; }   // (only the grid split matters here)
+    if (params->pyramid_prepared) { plan = concurrent_plan(ws, B, params->metrics != 0); plan.pyr_prelaunched = false; }   // (only the grid split matters here)
     return run_reduce(pred, gt, mask, B, H, W, *params, ws, (cudaStream_t)stream, plan);
 }
 
@@ -729,7 +731,7 @@ int cadl_stack_prepare(const float* pred, const float* gt, int B, int H, int W, 
         a.inv_nx[s] = nx > 0.0 ? (float)(1.0 / nx) : 0.f;
         a.inv_ny[s] = ny > 0.0 ? (float)(1.0 / ny) : 0.f;
     }
-    return cuda_rc(prelaunch_pyramid(a, ws, (cudaStream_t)stream, aux, concurrent_plan(ws, B)));
+    return cuda_rc(prelaunch_pyramid(a, ws, (cudaStream_t)stream, aux, concurrent_plan(ws, B, params->metrics != 0)));
 }
 
 int cadl_stack_grad(const float* pred, const float* gt, const float* rgb, const float* K, const uint8_t* mask,
@@ -743,7 +745,7 @@ int cadl_stack_grad(const float* pred, const float* gt, const float* rgb, const 
     if (params->pyramid_prepared) {
         AuxStream* aux = aux_for_current_device();
         if (!aux) return CADL_ERR_UNSUPPORTED;
-        plan = concurrent_plan(ws, B);
+        plan = concurrent_plan(ws, B, params->metrics != 0);
         cudaError_t e = cudaStreamWaitEvent((cudaStream_t)stream, aux->join, 0);
         if (e != cudaSuccess) return cuda_rc(e);
         // (if the gradient part then takes another kernel -- e.g. an unaligned gradient buffer -- the prepared
@@ -770,7 +772,7 @@ int cadl_stack_fwd_bwd(const float* pred, const float* gt, const float* rgb, con
         bool nothing = false;
         if (fill_b_args(a, pred, gt, rgb, K, mask, B, H, W, *params, grad_pred, results, ws, &nothing) == CADL_OK && !nothing &&
             stream_path_ok(a, *params, ws) && (aux = aux_for_current_device()) != nullptr) {
-            plan = concurrent_plan(ws, B);
+            plan = concurrent_plan(ws, B, params->metrics != 0);
             plan.pyr_prelaunched = false;
             cudaError_t e = prelaunch_pyramid(a, ws, st, aux, plan);
             if (e != cudaSuccess) return cuda_rc(e);

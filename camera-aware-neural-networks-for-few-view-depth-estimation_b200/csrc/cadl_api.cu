@@ -343,7 +343,7 @@ cudaError_t launch_stream(PhaseBArgs& a, const Ws& ws, cudaStream_t st, bool* of
     StreamArgs sa{};
     sa.c1 = py.c1; sa.nstrip = (a.W + 127) / 128;
     const int num_sms = num_sms_cached();
-    const int wave = 2 * num_sms * (kThreadsB / 32);                 // resident warps: 2 CTAs x 8 warps per SM (128 registers)
+    const int wave = kStreamCtasPerSm * num_sms * (kStreamThreads / 32);            // resident warps: 2 CTAs x 8 warps per SM (128 registers)
     const int SR = sa.nstrip * a.H;
     sa.cpi = wave / a.B > 0 ? wave / a.B : 1;
     if (sa.cpi > ws.L.stream_cpi) sa.cpi = ws.L.stream_cpi;         // workspace sized for this many rows per image
@@ -355,11 +355,11 @@ cudaError_t launch_stream(PhaseBArgs& a, const Ws& ws, cudaStream_t st, bool* of
     sa.trace = g_trace; sa.trace_cap = g_trace_cap;
     const bool defer = (F & FB_SMOOTH) && a.grad;    // results + offset in stream_finish_kernel
     sa.finalize_inline = defer ? 0 : 1;
-    int grid = (a.B * sa.cpi + kThreadsB / 32 - 1) / (kThreadsB / 32);
-    if (grid > 2 * num_sms) grid = 2 * num_sms;
+    int grid = (a.B * sa.cpi + kStreamThreads / 32 - 1) / (kStreamThreads / 32);
+    if (grid > kStreamCtasPerSm * num_sms) grid = kStreamCtasPerSm * num_sms;
     const bool pdl_s = pdl && !plan.pyr_prelaunched;
-    if (a.mask) e = launch_pdl(phase_b_stream_kernel<F, true>, dim3(grid), dim3(kThreadsB), st, pdl_s, a, sa);
-    else e = launch_pdl(phase_b_stream_kernel<F, false>, dim3(grid), dim3(kThreadsB), st, pdl_s, a, sa);
+    if (a.mask) e = launch_pdl(phase_b_stream_kernel<F, true>, dim3(grid), dim3(kStreamThreads), st, pdl_s, a, sa);
+    else e = launch_pdl(phase_b_stream_kernel<F, false>, dim3(grid), dim3(kStreamThreads), st, pdl_s, a, sa);
     if (e != cudaSuccess) return e;
     kt_mark(st, "phase_b_stream_kernel");
     if (defer) {

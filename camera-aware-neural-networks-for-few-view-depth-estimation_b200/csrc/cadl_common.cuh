@@ -59,8 +59,20 @@ struct WsLayout {
     int pyr_blocks;   // CTAs of pyr_pool_kernel / pyr_coef_kernel (0: shape not a multiple of 8)
 };
 
+// CTA shape of phase_b_stream_kernel.  Unconstrained the kernel wants 167 registers; 2 x 192 threads per SM give it
+// that (12 warps/SM, no spills, nothing re-materialised per row).  Measured us/step at config 3: 2 x 192 -> 192.0,
+// 3 x 128 -> 192.8, 4 x 96 -> 192.5, 2 x 256 (128 registers, 16 warps) -> 195.6, 2 x 160 -> 211.0,
+// 2 x 320 (96 registers, spills) -> 222.9, 2 x 384 -> 232.1.
+#ifndef CADL_STREAM_THREADS
+#define CADL_STREAM_THREADS 192
+#endif
+#ifndef CADL_STREAM_MINB
+#define CADL_STREAM_MINB 2
+#endif
+constexpr int kStreamCtasPerSm = CADL_STREAM_MINB;
+constexpr int kStreamThreads = CADL_STREAM_THREADS;   // threads per CTA of phase_b_stream_kernel (2 CTAs per SM)
 constexpr int kPointBlocks = 148 * 8;       // partial rows of the pointwise kernels
-constexpr int kStreamWaveWarps = 160 * 16;  // upper bound of the streaming kernel's resident warps (2 CTAs x 8 warps x <=160 SMs)
+constexpr int kStreamWaveWarps = 160 * CADL_STREAM_MINB * (CADL_STREAM_THREADS / 32);  // upper bound of the streaming kernel's resident warps (2 CTAs x 8 warps x <=160 SMs)
 
 constexpr int kThreadsA = 256;
 constexpr int kThreadsB = 256;

@@ -303,7 +303,7 @@ struct StreamRow {
 };
 
 template <int F, bool HAS_MASK>
-__global__ void __launch_bounds__(kThreadsB, 2) phase_b_stream_kernel(const PhaseBArgs a, const StreamArgs sa) {
+__global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm) phase_b_stream_kernel(const PhaseBArgs a, const StreamArgs sa) {
     __shared__ double s_d[8];
     __shared__ int s_last;
     constexpr bool SMOOTH = (F & FB_SMOOTH) != 0;
@@ -340,8 +340,8 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_stream_kernel(const Phas
     // resident wave (more than one per warp only for huge batches).  cadl_debug_set_trace shows warps finishing
     // within +-12 % of each other; handing the last quarter of each image out dynamically in 4-row chunks was
     // measured SLOWER (114 vs 104 us: every chunk restarts the two-row prologue with its loads exposed).
-    const int nwarps = gridDim.x * (kThreadsB / 32);
-    const int gwarp = blockIdx.x * (kThreadsB / 32) + (tid >> 5);
+    const int nwarps = gridDim.x * (kStreamThreads / 32);
+    const int gwarp = blockIdx.x * (kStreamThreads / 32) + (tid >> 5);
     const int nitems = a.B * sa.cpi;
     const int SR = sa.nstrip * H;                      // strip-rows per image  (< 2^31: nstrip * H <= H * W / 4)
     unsigned long long t_start = 0;

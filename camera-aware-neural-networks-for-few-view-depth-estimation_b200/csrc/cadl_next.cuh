@@ -32,6 +32,7 @@ struct PrepArgs {
     const float* aug;
 };
 
+template <bool AUG>      // AUG = false: plain resizeSample, every augmentation branch compiled out
 __global__ void __launch_bounds__(256) batch_prep_kernel(const PrepArgs a) {
     const int b = blockIdx.z;
     const int y = blockIdx.y;
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(256) batch_prep_kernel(const PrepArgs a) {
     int cx0 = 0, cy0 = 0, cw = a.w, ch = a.h;
     bool flip = false, jitter = false;
     float contrast = 1.f, brightness = 1.f;
-    if (a.aug) {
+    if constexpr (AUG) {
         const float* g = a.aug + (size_t)b * 8;
         if (__ldg(g + 2) > 0.f) { cx0 = (int)__ldg(g + 0); cy0 = (int)__ldg(g + 1); cw = (int)__ldg(g + 2); ch = (int)__ldg(g + 3); }
         flip = __ldg(g + 4) != 0.f;
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(256) batch_prep_kernel(const PrepArgs a) {
         float k[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) k[i] = Ki[i];
-        if (a.aug && __ldg(a.aug + (size_t)b * 8 + 2) > 0.f) {   // :411-414  principal point follows the crop
+        if (AUG && __ldg(a.aug + (size_t)b * 8 + 2) > 0.f) {   // :411-414  principal point follows the crop
             k[2] = k[2] - (float)cx0;
             k[5] = k[5] - (float)cy0;
         }
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(256) batch_prep_kernel(const PrepArgs a) {
     if (x >= a.W) return;
     const float scale_h = (float)ch / (float)a.H, scale_w = (float)cw / (float)a.W;
     // column of the (cropped, flipped) image -> column of the input
-    auto col = [&](int xc) { return cx0 + (flip ? cw - 1 - xc : xc); };
+    auto col = [&](int xc) { return AUG ? cx0 + (flip ? cw - 1 - xc : xc) : xc; };
     // nearest (depth): sunrgbd_loader.cpp:461-467
     {
         const int sy = min((int)floorf((float)y * scale_h), ch - 1);
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(256) batch_prep_kernel(const PrepArgs a) {
     // colour jitter acts on the pixels before the resize: clamp(rgb * contrast + brightness - 1, 0, 1), one rounding per op
     auto tap = [&](const float* src, int yy, int xx) {
         float v = __ldg(src + (size_t)(cy0 + yy) * a.w + xx);
-        if (jitter) {
+        if (AUG && jitter) {
             v = __fadd_rn(__fadd_rn(__fmul_rn(v, contrast), brightness), -1.0f);
             v = clamp_nan(v, 0.f, 1.f);
         }
@@ -113,7 +114,8 @@ __global__ void accumulate_kernel(const float* values, int n, double weight, dou
 
 inline cudaError_t launch_batch_prep(const PrepArgs& a, cudaStream_t st) {
     dim3 grid((a.W + 255) / 256, a.H, a.B);
-    batch_prep_kernel<<<grid, 256, 0, st>>>(a);
+    if (a.aug) batch_prep_kernel<true><<<grid, 256, 0, st>>>(a);
+    else batch_prep_kernel<false><<<grid, 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -98,8 +98,10 @@ __global__ void __launch_bounds__(256) batch_prep_kernel(const PrepArgs a) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const float* src = a.rgb_in + ((size_t)b * 3 + c) * a.h * a.w;
-        const float v = ly0 * (lx0 * tap(src, y0, c0) + lx1 * tap(src, y0, c1)) +
-                        ly1 * (lx0 * tap(src, y1, c0) + lx1 * tap(src, y1, c1));
+        // explicit roundings (no FMA contraction): both instantiations and the CPU restatement round alike
+        const float top = __fadd_rn(__fmul_rn(lx0, tap(src, y0, c0)), __fmul_rn(lx1, tap(src, y0, c1)));
+        const float bot = __fadd_rn(__fmul_rn(lx0, tap(src, y1, c0)), __fmul_rn(lx1, tap(src, y1, c1)));
+        const float v = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
         a.rgb_out[(((size_t)b * 3 + c) * a.H + y) * a.W + x] = v;
     }
 }

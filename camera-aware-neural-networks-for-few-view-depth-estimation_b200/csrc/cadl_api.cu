@@ -343,7 +343,7 @@ cudaError_t launch_stream(PhaseBArgs& a, const Ws& ws, cudaStream_t st, bool* of
     StreamArgs sa{};
     sa.c1 = py.c1; sa.nstrip = (a.W + 127) / 128;
     const int num_sms = num_sms_cached();
-    const int wave = kStreamCtasPerSm * num_sms * (kStreamThreads / 32);            // resident warps: 2 CTAs x 8 warps per SM (128 registers)
+    const int wave = kStreamCtasPerSm * num_sms * (kStreamThreads / 32);            // resident warps: 2 CTAs x 6 warps per SM (cadl_common.cuh)
     const int SR = sa.nstrip * a.H;
     sa.cpi = wave / a.B > 0 ? wave / a.B : 1;
     if (sa.cpi > ws.L.stream_cpi) sa.cpi = ws.L.stream_cpi;         // workspace sized for this many rows per image

@@ -72,7 +72,7 @@ struct WsLayout {
 constexpr int kStreamCtasPerSm = CADL_STREAM_MINB;
 constexpr int kStreamThreads = CADL_STREAM_THREADS;   // threads per CTA of phase_b_stream_kernel (2 CTAs per SM)
 constexpr int kPointBlocks = 148 * 8;       // partial rows of the pointwise kernels
-constexpr int kStreamWaveWarps = 160 * CADL_STREAM_MINB * (CADL_STREAM_THREADS / 32);  // upper bound of the streaming kernel's resident warps (2 CTAs x 8 warps x <=160 SMs)
+constexpr int kStreamWaveWarps = 160 * CADL_STREAM_MINB * (CADL_STREAM_THREADS / 32);  // upper bound of the streaming kernel's resident warps (CTAs per SM x warps per CTA x <=160 SMs)
 
 constexpr int kThreadsA = 256;
 constexpr int kThreadsB = 256;

@@ -17,7 +17,7 @@
 //   phase_b_stream_kernel   the full-resolution pass alone: one warp = 128 columns marching down ~32 rows, logs
 //                     evaluated in registers as each row arrives, every edge once, no shared memory, no barriers,
 //                     no halo except one pixel per warp end.  Each image's strip-rows are divided evenly over the
-//                     warps of ONE resident wave (2 CTAs x 8 warps per SM), so there is no tail of partial waves
+//                     warps of ONE resident wave (2 CTAs x 6 warps per SM), so there is no tail of partial waves
 //                     (claiming 8-row chunks dynamically was measured slower: +10 % instructions for the extra
 //                     prologues and a tail of up to one chunk out of four).  The warp that finishes an image folds
 //                     that image's partial rows into one, so the kernel-final reduction reads B rows, not thousands

@@ -271,7 +271,12 @@ struct StreamArgs {
     unsigned long long* trace;   // cadl_debug_set_trace: per warp {smid, start ns, end ns, items}; null = off
     int trace_cap;
 };
-constexpr int kStreamPrefetchRows = 3;     // L2 prefetch distance inside a chunk
+// L2 prefetch distance in rows, ahead of the one-row register prefetch (us/step at config 3: 1 -> 196, 2 -> 191.5,
+// 3 -> 193.1, 5 -> 192.8, 8 -> 194.2)
+#ifndef CADL_STREAM_PF
+#define CADL_STREAM_PF 2
+#endif
+constexpr int kStreamPrefetchRows = CADL_STREAM_PF;     // L2 prefetch distance inside a chunk
 
 // Sum of one image's chunk rows in a fixed order (lane-strided, fixed shuffle tree), by the warp that finished the image.
 __device__ __noinline__ void fold_image_rows(const double* rows, int n, double* out, unsigned int* cnt, int lane) {

@@ -366,7 +366,9 @@ cudaError_t launch_stream(PhaseBArgs& a, const Ws& ws, cudaStream_t st, bool* of
         const int HW = a.H * a.W;
         const int vec = (HW % 4 == 0) && aligned(a.grad, 16);
         int bx = (HW / 4 + 255) / 256;
-        int cap = (148 * 8 + a.B - 1) / a.B;
+        // one resident wave: the kernel holds 3 CTAs of 256 threads per SM (us/step at config 3 by CTAs per image:
+        // 9 -> 196.1, 13 -> 190.5, 18 -> 194.7, 27 -> 191.6, 37 -> 192.0, 74 -> 193.5)
+        int cap = (3 * num_sms_cached()) / (a.B + 1);
         if (bx > cap) bx = cap;
         if (bx < 1) bx = 1;
         e = launch_pdl(stream_finish_kernel, dim3(bx, a.B + 1), dim3(256), st, pdl, a, vec);

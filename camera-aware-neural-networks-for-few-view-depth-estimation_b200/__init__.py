@@ -17,7 +17,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)
-LIBCADL_PATH = os.path.join(_HERE, "csrc", "libcadl.so")
+LIBCADL_PATH = os.environ.get("CADL_LIB", os.path.join(_HERE, "csrc", "libcadl.so"))   # CADL_LIB: tuning builds (profiles/)
 LIBHOST_PATH = os.path.join(_HERE, "host", "libcadl_host.so")
 
 TERM_SI, TERM_GRAD, TERM_SMOOTH, TERM_REPROJ, TERM_ALL = 1, 2, 4, 8, 15
@@ -65,7 +65,7 @@ ABI_SYMBOLS = (
     "cadl_si_fwd_bwd", "cadl_gradmatch_fwd_bwd", "cadl_smooth_fwd_bwd", "cadl_reproj_fwd_bwd",
     "cadl_scale_grad", "cadl_metrics", "cadl_rays_from_K", "cadl_photometric_fwd_bwd",
     "cadl_batch_prep", "cadl_clip_workspace_bytes", "cadl_clip_grad_norm", "cadl_debug_set_trace",
-    "cadl_debug_kernel_times",
+    "cadl_debug_kernel_times", "cadl_debug_set_int",
     "cadl_batch_augment", "cadl_accumulate", "cadl_stack_prepare",
     "cadl_p2p_inbox_bytes", "cadl_p2p_alloc", "cadl_p2p_open", "cadl_p2p_close", "cadl_stats_exchange", "cadl_p2p_error",
 )
@@ -120,6 +120,8 @@ def lib() -> C.CDLL:
     L.cadl_clip_grad_norm.argtypes = [vp, vp, vp, C.c_int, C.c_longlong, C.c_float, f32p, vp, C.c_size_t, C.c_int, vp]
     L.cadl_debug_force_generic.argtypes = [C.c_int]
     L.cadl_debug_force_generic.restype = None
+    L.cadl_debug_set_int.argtypes = [C.c_int, C.c_int]
+    L.cadl_debug_set_int.restype = None
     L.cadl_debug_set_trace.argtypes = [C.c_void_p, C.c_int]
     L.cadl_debug_set_trace.restype = None
     L.cadl_selftest.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_float, vp, vp]

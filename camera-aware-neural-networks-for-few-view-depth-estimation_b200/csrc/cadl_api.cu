@@ -1,6 +1,7 @@
 // cadl C ABI (include/cadl.h): argument checks, workspace carving, kernel dispatch.
 // Built only for sm_100a; there is no host/CPU implementation behind these entry points.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -11,6 +12,7 @@
 #include "cadl_phase_b_fast.cuh"
 #include "cadl_phase_b_ws.cuh"
 #include "cadl_phase_b_stream.cuh"
+#include "cadl_stream3_host.h"
 #include "cadl_rays.cuh"
 #include "cadl_photometric.cuh"
 #include "cadl_next.cuh"
@@ -70,6 +72,7 @@ struct Ws {
     double* img_sm() const { return reinterpret_cast<double*>(base + L.img_sm); }
     float* img_off() const { return reinterpret_cast<float*>(base + L.img_off); }
     unsigned int* img_cnt() const { return reinterpret_cast<unsigned int*>(base + L.img_cnt); }
+    ImgRec* img_rec() const { return reinterpret_cast<ImgRec*>(base + L.img_rec); }
     bool has_pyr() const { return L.pyr_blocks > 0; }
     PyrArrays pyr() const {
         PyrArrays p;
@@ -87,6 +90,7 @@ int g_force_generic = 0;
 int g_force_tile = 0;
 int g_no_coop = 0;          // bit 6: reprojection alone keeps the separate count kernel (no cooperative launch)
 int g_no_overlap = 0;       // bit 5: pooled-pyramid kernels in line on the caller's stream instead of beside phase A
+int g_old_stream = 0;      // bit 7: round-1 streaming kernel + finish kernel instead of stream2_kernel
 int g_no_pdl = 0;           // bit 4: plain stream-ordered launches (no programmatic dependent launch)
 // cadl_debug_kernel_times: CUDA events between the launches of one cadl_stack_fwd_bwd call (debug / profiling aid)
 struct KTimes {
@@ -340,6 +344,25 @@ cudaError_t launch_stream(PhaseBArgs& a, const Ws& ws, cudaStream_t st, bool* of
         e = launch_pyramid(a, ws, st, nblk, pdl, pdl);
         if (e != cudaSuccess) return e;
     }
+    if (!g_old_stream && !g_trace && a.eps_grad >= 1e-30f && (!(F & FB_SI) || a.eps_si == a.eps_grad) &&
+        (!(F & FB_RP) || a.eps_rp == a.eps_grad)) {
+        // round-2 kernel: TMA row ring, two-tier logs, packed reprojection, smoothness offset applied in-kernel
+        // (cadl_stream3.cuh)
+        Stream3Args s3{};
+        s3.c1 = py.c1; s3.nstrip = (a.W + 127) / 128;
+        s3.pyr_rows = a.b_part + (size_t)a.B * BF_COUNT; s3.n_pyr_rows = nblk;
+        s3.img = ws.img_rec(); s3.done = &ws.hdr()->ticket_b; s3.epoch = &ws.hdr()->pad[0];
+        if (!(F & FB_SMOOTH) || stream3_fill_smooth(a, s3)) {
+            e = launch_stream3(F, a, s3, st);
+            if (e == cudaSuccess) {
+                kt_mark(st, "stream3_kernel");
+                *offset_done = true;
+                return cudaSuccess;
+            }
+            if (e != cudaErrorNotSupported && e != cudaErrorCooperativeLaunchTooLarge) return e;
+            cudaGetLastError();
+        }
+    }
     StreamArgs sa{};
     sa.c1 = py.c1; sa.nstrip = (a.W + 127) / 128;
     const int num_sms = num_sms_cached();
@@ -469,9 +492,21 @@ int run_reduce(const float* pred, const float* gt, const uint8_t* mask, int B, i
     a.vec_ok = ((H * W) % 4 == 0) && (!pred || aligned(pred, 16)) && (!gt || aligned(gt, 16)) &&
                (!mask || aligned(mask, 4));
     a.eps_si = p.eps_si; a.eps_rp = p.eps_reproj; a.min_d = p.min_depth; a.max_d = p.max_depth;
-    a.g_lo = p.min_depth > 0.25f ? p.min_depth : 0.25f;
-    a.p_lo = a.g_lo;
-    a.share_ok = (p.eps_si <= p.min_depth) && (p.max_depth <= 1000.0f) && (p.min_depth > 0.0f);
+    {
+        // guard bands of the delta thresholds in the log2 domain: two lg2.approx (2^-22 absolute each), the fp32
+        // rounding of their results and of the difference (ulp of the largest |log2 depth| in range)
+        float big = fabsf(log2f(p.max_depth > 0.f ? p.max_depth : 1.f));
+        const float lo = fabsf(log2f(p.min_depth > 1e-30f ? p.min_depth : 1e-30f));
+        if (lo > big) big = lo;
+        if (!(big > 4.f)) big = 4.f;
+        const float bw = 3.8e-6f * (big / 4.f);
+        for (int k = 0; k < 3; ++k) {
+            const float t = 0.32192809488736235f * (float)(k + 1), l = t - bw, h = t + bw;
+            uint32_t ul, uh;
+            memcpy(&ul, &l, 4); memcpy(&uh, &h, 4);
+            a.near_lo[k] = ul; a.near_span[k] = uh - ul;
+        }
+    }
     a.hdr = ws.hdr(); a.stats = ws.stats(); a.img_psum = ws.img_psum(); a.a_part = ws.a_part();
     dim3 grid(a.blocks_per_img, B);
     return cuda_rc(dispatch_a(f, a, grid, st));
@@ -641,6 +676,10 @@ int cadl_debug_kernel_times(int enable, float* ms_out, const char** names_out, i
     return n;
 }
 
+void cadl_debug_set_int(int key, int value) {
+    (void)key; (void)value;
+}
+
 void cadl_debug_set_trace(unsigned long long* dev_buf, int capacity_warps) {
     g_trace = dev_buf;
     g_trace_cap = dev_buf ? capacity_warps : 0;
@@ -653,6 +692,7 @@ void cadl_debug_force_generic(int on) {
     g_no_pdl = (on >> 4) & 1;
     g_no_overlap = (on >> 5) & 1;
     g_no_coop = (on >> 6) & 1;
+    g_old_stream = (on >> 7) & 1;
     g_use_ws = (on >> 2) & 1;
 }
 size_t cadl_sizeof_params(void) { return sizeof(cadl_params); }
@@ -794,6 +834,8 @@ int cadl_stack_fwd_bwd(const float* pred, const float* gt, const float* rgb, con
             cudaGetLastError();            // not co-resident on this device / this shape: two launches
         }
     }
+    // (Measured, not adopted: the metrics-only reduce pass BESIDE the gradient pass on the auxiliary stream -- 168 vs
+    //  158 us/step: the cooperative gradient kernel fills every SM's register file, so the two cannot share the SMs.)
     rc = run_reduce(pred, gt, mask, B, H, W, *params, ws, st, plan);
     if (rc) return rc;
     kt_mark(st, "phase_a_kernel");

@@ -52,7 +52,7 @@ struct WsHeader {
 };
 
 struct WsLayout {
-    size_t header, stats, img_psum, a_part, b_part, img_sm, img_off, img_cnt, total;
+    size_t header, stats, img_psum, a_part, b_part, img_sm, img_off, img_cnt, img_rec, total;
     size_t pyr_lp[3], pyr_lg[3], pyr_rq[3], pyr_c1;   // streaming fast path (cadl_phase_b_stream.cuh); 0 = absent
     int a_blocks_per_img, a_blocks, b_tiles;
     int stream_cpi;   // streaming kernel: static shares per image (one per warp of the resident wave)
@@ -116,6 +116,7 @@ __host__ inline WsLayout ws_layout(int B, int H, int W) {
     L.img_sm = o;   o = align_up(o + sizeof(double) * (size_t)B * 2, 256);
     L.img_off = o;  o = align_up(o + sizeof(float) * (size_t)B, 256);
     L.img_cnt = o;  o = align_up(o + sizeof(unsigned int) * (size_t)B, 256);   // chunks done per image (streaming kernel)
+    L.img_rec = o;  o = align_up(o + 128 * (size_t)B, 256);                    // ImgRec per image (cadl_stream3_host.h)
     for (int s = 0; s < 3; ++s) {
         const size_t cells = pyr ? (size_t)B * (H >> (s + 1)) * (W >> (s + 1)) : 0;
         L.pyr_lp[s] = pyr ? o : 0; o = align_up(o + sizeof(float) * cells, 256);

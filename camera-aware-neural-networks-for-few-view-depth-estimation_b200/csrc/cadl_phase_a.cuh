@@ -20,28 +20,18 @@ struct PhaseAArgs {
     int blocks_per_img;
     int vec_ok;
     float eps_si, eps_rp, min_d, max_d;
-    float g_lo, p_lo;    // fast-metrics thresholds: max(min_d, 0.25)
-    int share_ok;        // eps_si <= min_d && max_d <= 1000: both metric variants can reuse the SI logs
+    unsigned near_lo[3], near_span[3];   // guard bands around k log2(1.25) as bit patterns: exact delta counts
     WsHeader* hdr;
     double* stats;
     double* img_psum;
     double* a_part;
 };
 
-// delta-threshold counting with the reference's IEEE semantics at SFU cost: the quotients come from
-// rcp.approx (<= 2 ulp), and only when max(p/g, g/p) lies within a guard band of a threshold (probability
-// ~1e-5 per pixel) are the two IEEE divisions of depth_metrics.h:221 / trainer :433 actually performed.
-__device__ __forceinline__ float ratio_for_thresholds(float p, float g, float rp, float rg) {
-    float ratio = fmaxf(p * rg, g * rp);
-    // guard bands of 34 / 42 / 51 ulps (4e-6, 5e-6, 6e-6) around 1.25, 1.5625, 1.953125, tested on the bit
-    // patterns: one integer subtract + one unsigned compare each.  (A NaN or infinite ratio is outside every band
-    // and compares false against the thresholds exactly like the IEEE quotients would.)
-    const int u = __float_as_int(ratio);
-    const bool near = ((unsigned)(u - (0x3FA00000 - 34)) <= 68u) || ((unsigned)(u - (0x3FC80000 - 42)) <= 84u) ||
-                      ((unsigned)(u - (0x3FFA0000 - 51)) <= 102u);
-    if (near) ratio = fmaxf(__fdiv_rn(p, g), __fdiv_rn(g, p));
-    return ratio;
-}
+// Logs in phase A feed sums only (nothing here decides a sign), so they are lg2.approx (one MUFU) in log2 units and
+// the per-block sums are converted once: x ln2, x ln2^2, x log10(2).  Round 1 evaluated a logf replica per value
+// (~16 instructions each); the 1e-5 tolerance of the losses and metrics leaves four orders of magnitude of room.
+constexpr float kLn2f = 0.693147180559945309f;
+constexpr float kLog2_125 = 0.32192809488736235f;        // log2(1.25): the delta thresholds are 1.25^k
 
 // Per-thread accumulators of phase A.  Both metric variants take the same per-pixel terms whenever
 // min < gt < max and pred needs no clamping (the trainers' +1e-8 inside the log is applied as an exact
@@ -49,23 +39,23 @@ __device__ __forceinline__ float ratio_for_thresholds(float p, float g, float rp
 // (gt outside (min,max) but > 0, or pred outside [min,max]) are evaluated separately for the trainer variant
 // and kept in per-thread shared-memory slots so they cost no registers.
 struct AccA {
-    float psum, si_s, si_q;
+    float psum, si_s, si_q;                          // si_s, si_q in log2 units
     unsigned si_n, rp_n;
-    float c_absrel, c_sqrel, c_sq, c_logsq;          // eval == train
+    float c_absrel, c_sqrel, c_sq, c_logsq;          // eval == train   (c_logsq in log2^2 units)
     unsigned c_n, c_c1, c_c2, c_c3;
-    float e_abs, e_l10, e_sump, e_sumg;              // eval-only quantities
-    float t_logsq;                                   // train: correction of sum ld^2 for the +1e-8 inside the logs
+    float e_abs, e_l10, e_sump, e_sumg;              // eval-only quantities (e_l10 in log2 units)
+    float t_logsq;                                   // train: correction of sum ld^2 for the +1e-8 inside the logs (natural units)
 };
 constexpr int kToSlots = 8;   // train-only slow path: absrel, sqrel, sq, logsq, n, c1, c2, c3
 
 template <int F, bool HAS_MASK>
-__device__ __forceinline__ void phase_a_px(float p, float g, float lp, float lg, bool um, const PhaseAArgs& a,
-                                           float Lmin, float Lmax, AccA& A, float* s_to) {
+__device__ __forceinline__ void phase_a_px(float p, float g, bool um, const PhaseAArgs& a, AccA& A, float* s_to) {
     if constexpr (F & FA_PSUM) A.psum += p;                 // depth_loss.h:192 (mean over H,W)
     if constexpr (F & FA_SI) {
         // depth_loss.h:38-47
         const bool m = HAS_MASK ? um : (g > a.eps_si);
-        const float d = m ? lp - lg : 0.f;
+        const float d2 = lg2_approx(clamp_nan(p, a.eps_si, 1000.0f)) - lg2_approx(clamp_nan(g, a.eps_si, 1000.0f));
+        const float d = m ? d2 : 0.f;
         A.si_n += m ? 1u : 0u;
         A.si_s += d;
         A.si_q = fmaf(d, d, A.si_q);
@@ -76,38 +66,47 @@ __device__ __forceinline__ void phase_a_px(float p, float g, float lp, float lg,
     }
     if constexpr ((F & (FA_EV | FA_TR)) != 0) {
         constexpr bool EV = (F & FA_EV) != 0, TR = (F & FA_TR) != 0;
-        // eval terms, pred clamped AFTER masking (depth_metrics.h:154-161, :66); log(pc) without a branch:
-        // inside [min,max] it is the SI log, outside it is one of two constants.
+        // eval terms, pred clamped AFTER masking (depth_metrics.h:154-161, :66)
         const bool ev_ok = (g > a.min_d) && (g < a.max_d) && (HAS_MASK ? um : true);
         const float pc = clamp_nan(p, a.min_d, a.max_d);
-        const float lpe = (p < a.min_d) ? Lmin : ((p > a.max_d) ? Lmax : lp);
         const float rg = rcp_approx(g);
         const float diff = pc - g, ad = fabsf(diff), sq = diff * diff;              // :170-199 (pow(x,2) == x*x)
-        const float ld = lpe - lg;
+        const float ld = lg2_approx(pc) - lg2_approx(g);                            // log2 units; g > min_d > 0 where it counts
         if (ev_ok) {
-            const float ratio = ratio_for_thresholds(pc, g, rcp_approx(pc), rg);    // :221
+            // delta thresholds (:221-229, trainer :433): max(p/g, g/p) < 1.25^k  <=>  |log2 p - log2 g| < k log2 1.25.
+            // Only when |ld| lies within a guard band of a threshold (the error of the two approximate logs; ~1e-5
+            // of the pixels) are the reference's two IEEE divisions actually performed.
+            const float ald = fabsf(ld);
+            const unsigned u = (unsigned)__float_as_int(ald);
+            const bool near = (u - a.near_lo[0] <= a.near_span[0]) || (u - a.near_lo[1] <= a.near_span[1]) ||
+                              (u - a.near_lo[2] <= a.near_span[2]);
+            bool b1 = ald < kLog2_125, b2 = ald < 2.f * kLog2_125, b3 = ald < 3.f * kLog2_125;
+            if (near) {
+                const float ratio = fmaxf(__fdiv_rn(pc, g), __fdiv_rn(g, pc));
+                b1 = ratio < 1.25f; b2 = ratio < 1.5625f; b3 = ratio < 1.953125f;
+            }
             A.c_absrel = fmaf(ad, rg, A.c_absrel);
             A.c_sqrel = fmaf(sq, rg, A.c_sqrel);
             A.c_sq += sq;
             A.c_logsq = fmaf(ld, ld, A.c_logsq);
             A.c_n += 1u;
-            A.c_c1 += (ratio < 1.25f) ? 1u : 0u;                                    // :224-229
-            A.c_c2 += (ratio < 1.5625f) ? 1u : 0u;
-            A.c_c3 += (ratio < 1.953125f) ? 1u : 0u;
+            A.c_c1 += b1 ? 1u : 0u;
+            A.c_c2 += b2 ? 1u : 0u;
+            A.c_c3 += b3 ? 1u : 0u;
             if constexpr (EV) {
                 A.e_abs += ad;
-                A.e_l10 += fabsf(ld);                                               // x log10(e) at the end (:206)
+                A.e_l10 += ald;                                                     // x log10(2) at the end (:206)
                 A.e_sump += pc;
                 A.e_sumg += g;
             }
             if constexpr (TR) {
                 // trainer :429: log(x + 1e-8).  Only x < 0.25 changes under +1e-8f (half an ulp of 0.25 is 1.5e-8);
                 // there (x + 1e-8f) - x is exact and log(x + dx) = log x + dx/x to far below one ulp, so the train
-                // variant adds  (ld + c)^2 - ld^2 = c (2 ld + c)  to the common sum.  Rare branch.
+                // variant adds  (ld + c)^2 - ld^2 = c (2 ld + c)  to the common sum (natural-log units).  Rare branch.
                 if ((p < 0.25f || g < 0.25f) && pc == p) {
                     const float dp = (p + 1e-8f) - p, dg = (g + 1e-8f) - g;
                     const float c = fmaf(dp, rcp_approx(p), -dg * rg);
-                    A.t_logsq = fmaf(c, fmaf(2.f, ld, c), A.t_logsq);
+                    A.t_logsq = fmaf(c, fmaf(2.f * kLn2f, ld, c), A.t_logsq);
                 }
             }
         }
@@ -122,10 +121,11 @@ __device__ __forceinline__ void phase_a_px(float p, float g, float lp, float lg,
                 // "to" = train-only additions; where the pixel was also counted as common (ev_ok, clamped
                 // pred) the common contribution is taken back out so train = common + to stays exact in form
                 const float sgn = ev_ok ? 1.f : 0.f;
+                const float ldn = ld * kLn2f;                                        // what the common sum received (natural units)
                 s_to[0 * kThreadsA + t] += adt * rg - sgn * ad * rg;
                 s_to[1 * kThreadsA + t] += sqt * rg - sgn * sq * rg;
                 s_to[2 * kThreadsA + t] += sqt - sgn * sq;
-                s_to[3 * kThreadsA + t] += ldt * ldt;
+                s_to[3 * kThreadsA + t] += ldt * ldt - sgn * ldn * ldn;
                 const float rc = ev_ok ? fmaxf(__fdiv_rn(pc, g), __fdiv_rn(g, pc)) : 3.0f;
                 s_to[4 * kThreadsA + t] += 1.f - sgn;
                 s_to[5 * kThreadsA + t] += ((rt < 1.25f) ? 1.f : 0.f) - sgn * ((rc < 1.25f) ? 1.f : 0.f);
@@ -138,19 +138,9 @@ __device__ __forceinline__ void phase_a_px(float p, float g, float lp, float lg,
 
 template <int F, bool HAS_MASK>
 __device__ __forceinline__ void phase_a_quad(const float (&p)[4], const float (&g)[4], const bool (&um)[4],
-                                             const PhaseAArgs& a, float Lmin, float Lmax, AccA& A, float* s_to) {
-    float lp[4] = {0.f, 0.f, 0.f, 0.f}, lg[4] = {0.f, 0.f, 0.f, 0.f};
-    if constexpr ((F & (FA_SI | FA_EV | FA_TR)) != 0) {
+                                             const PhaseAArgs& a, AccA& A, float* s_to) {
 #pragma unroll
-        for (int k = 0; k < 4; k += 2) {
-            const float2 a2 = log_exact2(make_float2(clamp_nan(p[k], a.eps_si, 1000.0f), clamp_nan(p[k + 1], a.eps_si, 1000.0f)));
-            const float2 b2 = log_exact2(make_float2(clamp_nan(g[k], a.eps_si, 1000.0f), clamp_nan(g[k + 1], a.eps_si, 1000.0f)));
-            lp[k] = a2.x; lp[k + 1] = a2.y;                  // depth_loss.h:43-47
-            lg[k] = b2.x; lg[k + 1] = b2.y;
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) phase_a_px<F, HAS_MASK>(p[k], g[k], lp[k], lg[k], um[k], a, Lmin, Lmax, A, s_to);
+    for (int k = 0; k < 4; ++k) phase_a_px<F, HAS_MASK>(p[k], g[k], um[k], a, A, s_to);
 }
 
 // Deterministic block-wide sum of one double per thread (fixed shuffle/tree order).
@@ -187,8 +177,6 @@ __global__ void __launch_bounds__(kThreadsA, 4) phase_a_kernel(const PhaseAArgs 
     memset(&A, 0, sizeof(A));
 #pragma unroll
     for (int q = 0; q < kToSlots; ++q) s_to[q * kThreadsA + tid] = 0.f;   // private slots: no sync needed
-    // log(min_depth), log(max_depth): what log(clamp(pred)) is outside [min,max]
-    const float Lmin = (F & (FA_EV | FA_TR)) ? logf(a.min_d) : 0.f, Lmax = (F & (FA_EV | FA_TR)) ? logf(a.max_d) : 0.f;
 
     if (a.vec_ok) {
         const int nvec = a.HW >> 2;
@@ -217,7 +205,7 @@ __global__ void __launch_bounds__(kThreadsA, 4) phase_a_kernel(const PhaseAArgs 
                 if (i + u * kThreadsA < v1) {
                     const float pp[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w}, gg[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
                     const bool mm[4] = {uv[u].x != 0, uv[u].y != 0, uv[u].z != 0, uv[u].w != 0};
-                    phase_a_quad<F, HAS_MASK>(pp, gg, mm, a, Lmin, Lmax, A, s_to);
+                    phase_a_quad<F, HAS_MASK>(pp, gg, mm, a, A, s_to);
                 }
             }
         }
@@ -228,12 +216,7 @@ __global__ void __launch_bounds__(kThreadsA, 4) phase_a_kernel(const PhaseAArgs 
             float p = NEED_P ? __ldg(a.pred + base + i) : 0.f;
             float g = NEED_G ? __ldg(a.gt + base + i) : 0.f;
             bool um = has_mask ? (__ldg(a.mask + base + i) != 0) : true;
-            float lp = 0.f, lg = 0.f;
-            if constexpr ((F & (FA_SI | FA_EV | FA_TR)) != 0) {
-                lp = log_exact(clamp_nan(p, a.eps_si, 1000.0f));
-                lg = log_exact(clamp_nan(g, a.eps_si, 1000.0f));
-            }
-            phase_a_px<F, HAS_MASK>(p, g, lp, lg, um, a, Lmin, Lmax, A, s_to);
+            phase_a_px<F, HAS_MASK>(p, g, um, a, A, s_to);
         }
     }
 
@@ -241,15 +224,15 @@ __global__ void __launch_bounds__(kThreadsA, 4) phase_a_kernel(const PhaseAArgs 
     float af[AF_COUNT];
     unsigned ai[AI_COUNT];
     constexpr bool EVc = (F & FA_EV) != 0, TRc = (F & FA_TR) != 0;
-    af[AF_SI_S] = A.si_s; af[AF_SI_Q] = A.si_q; af[AF_PSUM] = A.psum;
+    af[AF_SI_S] = A.si_s * kLn2f; af[AF_SI_Q] = A.si_q * (kLn2f * kLn2f); af[AF_PSUM] = A.psum;      // log2 -> natural units
     af[AF_EV_ABSREL] = EVc ? A.c_absrel : 0.f; af[AF_EV_SQREL] = EVc ? A.c_sqrel : 0.f;
-    af[AF_EV_SQ] = EVc ? A.c_sq : 0.f; af[AF_EV_LOGSQ] = EVc ? A.c_logsq : 0.f;
-    af[AF_EV_ABS] = A.e_abs; af[AF_EV_LOG10] = A.e_l10 * 0.43429448190325182765f;   // log10 x = ln x / ln 10
+    af[AF_EV_SQ] = EVc ? A.c_sq : 0.f; af[AF_EV_LOGSQ] = EVc ? A.c_logsq * (kLn2f * kLn2f) : 0.f;
+    af[AF_EV_ABS] = A.e_abs; af[AF_EV_LOG10] = A.e_l10 * 0.30102999566398119521f;   // log10 x = log2 x * log10(2)
     af[AF_EV_SUMP] = A.e_sump; af[AF_EV_SUMG] = A.e_sumg;
     af[AF_TR_ABSREL] = TRc ? A.c_absrel + s_to[0 * kThreadsA + tid] : 0.f;
     af[AF_TR_SQREL] = TRc ? A.c_sqrel + s_to[1 * kThreadsA + tid] : 0.f;
     af[AF_TR_SQ] = TRc ? A.c_sq + s_to[2 * kThreadsA + tid] : 0.f;
-    af[AF_TR_LOGSQ] = TRc ? A.c_logsq + A.t_logsq + s_to[3 * kThreadsA + tid] : 0.f;
+    af[AF_TR_LOGSQ] = TRc ? A.c_logsq * (kLn2f * kLn2f) + A.t_logsq + s_to[3 * kThreadsA + tid] : 0.f;
     ai[AI_SI_N] = A.si_n; ai[AI_RP_N] = A.rp_n;
     ai[AI_EV_N] = EVc ? A.c_n : 0u; ai[AI_EV_C1] = EVc ? A.c_c1 : 0u;
     ai[AI_EV_C2] = EVc ? A.c_c2 : 0u; ai[AI_EV_C3] = EVc ? A.c_c3 : 0u;
@@ -391,7 +374,13 @@ __global__ void __launch_bounds__(kThreadsA, 4) phase_a_kernel(const PhaseAArgs 
             case AI_TR_C3: st = ST_TR_C3; break;
             default: break;
         }
-        if (st >= 0) a.stats[st] = (double)c;
+        // (only what this instantiation counts: a metrics-only pass may run beside the loss statistics' pass)
+        bool mine = true;
+        if (!(F & FA_SI) && tid == AI_SI_N) mine = false;
+        if (!(F & FA_RP) && tid == AI_RP_N) mine = false;
+        if (!(F & FA_EV) && tid >= AI_EV_N && tid <= AI_EV_C3) mine = false;
+        if (!(F & FA_TR) && tid >= AI_TR_N && tid <= AI_TR_C3) mine = false;
+        if (st >= 0 && mine) a.stats[st] = (double)c;
     }
     if (tid == 0) a.hdr->ticket_a = 0u;
 }

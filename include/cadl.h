@@ -104,6 +104,8 @@ const char* cadl_error_string(int code);
  * with the separate count kernel instead of the single cooperative launch.  All variants must
  * produce the same values.  Process-global; not for production use. */
 void cadl_debug_force_generic(int on);
+/* Tuning hook: key 0 = images per group of the streaming gradient kernel (default 8).  Process-global. */
+void cadl_debug_set_int(int key, int value);
 /* Debug trace of the streaming phase-B kernel: while dev_buf is non-NULL every warp (global index < capacity_warps)
  * writes {SM id, start globaltimer ns, end globaltimer ns, work items processed} as 4 x uint64 at dev_buf[4*warp].
  * NULL switches it off.  Process-global; profiling aid (profiles/trace_stream.py), not for production use. */

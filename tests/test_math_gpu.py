@@ -55,8 +55,8 @@ def test_fast_kernel_equals_generic_kernel(pkg, shape, terms):
             pkg.force_generic(False)
     (rf, gf), (rg, gg), (rc, gc), (rt, gt_), (rs, gs) = res
     assert torch.equal(gf, gt_)                            # plain fast kernel == warp-specialised, bit for bit
-    # streaming split vs tile kernel: the same operations per pixel, different reduction trees for the loss sums
-    assert float((gs - gf).abs().max()) <= 1e-7 * float(gf.abs().max()), float((gs - gf).abs().max())
+    # streaming kernel vs tile kernel: same signs; the pointwise terms use approximate logs there (1e-6, a tenth of the parity bar)
+    assert float((gs - gf).abs().max()) <= 1e-6 * float(gf.abs().max()), float((gs - gf).abs().max())
     for k in ("loss_total", "si_loss", "grad_loss", "smooth_loss", "reproj_loss"):
         assert rel_err(rs[k], rf[k]) <= 2e-6, (k, rs[k], rf[k])
     for k in ("loss_total", "si_loss", "grad_loss", "smooth_loss", "reproj_loss"):

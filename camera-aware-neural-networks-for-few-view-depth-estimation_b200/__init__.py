@@ -18,6 +18,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)
 LIBCADL_PATH = os.environ.get("CADL_LIB", os.path.join(_HERE, "csrc", "libcadl.so"))   # CADL_LIB: tuning builds (profiles/)
+LIBCADL_DBG_PATH = os.path.join(_HERE, "csrc", "libcadl_dbg.so")   # same sources with -DCADL_DEBUG: dispatch switches, per-launch timing
 LIBHOST_PATH = os.path.join(_HERE, "host", "libcadl_host.so")
 
 TERM_SI, TERM_GRAD, TERM_SMOOTH, TERM_REPROJ, TERM_ALL = 1, 2, 4, 8, 15
@@ -60,29 +61,44 @@ class CadlResults(C.Structure):
 # every symbol include/cadl.h declares (tests/test_abi.py checks the .so exports each one)
 ABI_SYMBOLS = (
     "cadl_default_params", "cadl_version", "cadl_sizeof_params", "cadl_sizeof_results", "cadl_error_string",
-    "cadl_debug_force_generic", "cadl_selftest", "cadl_workspace_bytes", "cadl_workspace_init",
+    "cadl_selftest", "cadl_workspace_bytes", "cadl_workspace_init",
     "cadl_stack_fwd_bwd", "cadl_stack_reduce", "cadl_stack_grad", "cadl_stats_offset", "cadl_stats_count",
     "cadl_si_fwd_bwd", "cadl_gradmatch_fwd_bwd", "cadl_smooth_fwd_bwd", "cadl_reproj_fwd_bwd",
     "cadl_scale_grad", "cadl_metrics", "cadl_rays_from_K", "cadl_photometric_fwd_bwd",
-    "cadl_batch_prep", "cadl_clip_workspace_bytes", "cadl_clip_grad_norm", "cadl_debug_set_trace",
-    "cadl_debug_kernel_times", "cadl_debug_set_int",
+    "cadl_batch_prep", "cadl_clip_workspace_bytes", "cadl_clip_grad_norm",
     "cadl_batch_augment", "cadl_accumulate", "cadl_stack_prepare",
     "cadl_p2p_inbox_bytes", "cadl_p2p_alloc", "cadl_p2p_open", "cadl_p2p_close", "cadl_stats_exchange", "cadl_p2p_error",
 )
 
-_lib = None
+_lib = None        # the product library
+_dbg = None        # the debug build (tests / profiling only)
+_active = None     # what the wrappers below call: the product library unless force_generic() selected a debug dispatch
 
 
 def lib() -> C.CDLL:
-    """Load libcadl.so (built by ``__graft_entry__.build()``); fail loudly if it is not there."""
+    """The library the wrappers call: libcadl.so (built by ``__graft_entry__.build()``), or -- while a debug dispatch
+    mode is selected with ``force_generic`` / ``kernel_times`` -- libcadl_dbg.so.  Fails loudly if it is not there."""
     global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIBCADL_PATH):
+    if _active is not None:
+        return _active
+    if _lib is None:
+        _lib = _load(LIBCADL_PATH)
+    return _lib
+
+
+def debug_lib() -> C.CDLL:
+    global _dbg
+    if _dbg is None:
+        _dbg = _load(LIBCADL_DBG_PATH, debug=True)
+    return _dbg
+
+
+def _load(path: str, debug: bool = False) -> C.CDLL:
+    if not os.path.exists(path):
         raise RuntimeError(
-            f"cadl: {LIBCADL_PATH} is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+            f"cadl: {path} is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'`"
             " (nvcc, sm_100a). There is no CPU fallback.")
-    L = C.CDLL(LIBCADL_PATH)
+    L = C.CDLL(path)
     vp, f32p, u8p = C.c_void_p, C.c_void_p, C.c_void_p
     L.cadl_default_params.argtypes = [C.POINTER(CadlParams)]
     L.cadl_default_params.restype = None
@@ -118,18 +134,16 @@ def lib() -> C.CDLL:
     L.cadl_batch_prep.argtypes = [f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, vp]
     L.cadl_clip_workspace_bytes.restype = C.c_size_t
     L.cadl_clip_grad_norm.argtypes = [vp, vp, vp, C.c_int, C.c_longlong, C.c_float, f32p, vp, C.c_size_t, C.c_int, vp]
-    L.cadl_debug_force_generic.argtypes = [C.c_int]
-    L.cadl_debug_force_generic.restype = None
-    L.cadl_debug_set_int.argtypes = [C.c_int, C.c_int]
-    L.cadl_debug_set_int.restype = None
-    L.cadl_debug_set_trace.argtypes = [C.c_void_p, C.c_int]
-    L.cadl_debug_set_trace.restype = None
+    if debug:
+        L.cadl_debug_force_generic.argtypes = [C.c_int]
+        L.cadl_debug_force_generic.restype = None
+        L.cadl_debug_kernel_times.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.c_int]
+        L.cadl_debug_kernel_times.restype = C.c_int
     L.cadl_selftest.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_float, vp, vp]
     for name in ABI_SYMBOLS:
         getattr(L, name)   # AttributeError here = the .so does not export what include/cadl.h declares
     if L.cadl_sizeof_params() != C.sizeof(CadlParams) or L.cadl_sizeof_results() != C.sizeof(CadlResults):
         raise RuntimeError("cadl: ctypes mirrors of cadl_params/cadl_results disagree with libcadl.so")
-    _lib = L
     return L
 
 
@@ -269,31 +283,31 @@ def metrics(pred, gt, mask=None, which: int = METRICS_EVAL | METRICS_TRAIN, min_
 
 
 def force_generic(on):
-    """Test hook (bit mask): 1 = route phase B through the generic kernel even for aligned shapes;
-    8 = the one-CTA-per-tile fast kernel instead of the streaming split (default for aligned shapes); with 8:
-    2 = stage tiles with cp.async instead of TMA, 4 = warp-specialised persistent tile kernel."""
-    lib().cadl_debug_force_generic(int(on))
+    """Test hook (bit mask, see include/cadl.h under CADL_DEBUG): a non-zero mode routes every following call through
+    libcadl_dbg.so with that dispatch (1 = generic phase-B kernel, 8 = one tile kernel instead of the pyramid +
+    streaming kernels, 8|2 = that kernel staged with cp.async, 16 = no programmatic dependent launch, 32 = pyramid
+    kernels in line, 64 = reprojection alone with the separate count kernel); 0 returns to the product library."""
+    global _active
+    on = int(on)
+    if on:
+        _active = debug_lib()
+        _active.cadl_debug_force_generic(on)
+    else:
+        if _dbg is not None:
+            _dbg.cadl_debug_force_generic(0)
+        _active = None
 
 
 def kernel_times(enable: bool = True):
-    """Switch per-launch event timing of stack_fwd_bwd on/off; returns [(kernel, ms)] of the last timed call."""
-    L = lib()
-    L.cadl_debug_kernel_times.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.c_int]
-    L.cadl_debug_kernel_times.restype = C.c_int
+    """Per-launch event timing of stack_fwd_bwd (debug library: selected while enabled); returns [(kernel, ms)] of the
+    last timed call."""
+    global _active
+    L = debug_lib()
     ms = (C.c_float * 12)()
     names = (C.c_char_p * 12)()
     n = L.cadl_debug_kernel_times(int(enable), ms, names, 12)
+    _active = L if enable else None
     return [(names[i].decode(), float(ms[i])) for i in range(n)]
-
-
-def set_trace(buf) -> None:
-    """Per-warp trace of the streaming phase-B kernel into an int64 CUDA tensor of shape (warps, 4):
-    {SM id, start ns, end ns, items}; None switches it off (profiles/trace_stream.py)."""
-    if buf is None:
-        lib().cadl_debug_set_trace(None, 0)
-    else:
-        assert buf.is_cuda and buf.dtype == torch.int64 and buf.is_contiguous() and buf.shape[1] == 4
-        lib().cadl_debug_set_trace(_ptr(buf), int(buf.shape[0]))
 
 
 def selftest(which: int, lo_bits: int, hi_bits: int, param: float = 0.0, device="cuda:0") -> int:

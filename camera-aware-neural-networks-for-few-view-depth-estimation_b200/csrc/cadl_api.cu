@@ -10,7 +10,6 @@
 #include "cadl_phase_a.cuh"
 #include "cadl_phase_b.cuh"
 #include "cadl_phase_b_fast.cuh"
-#include "cadl_phase_b_ws.cuh"
 #include "cadl_phase_b_stream.cuh"
 #include "cadl_stream3_host.h"
 #include "cadl_rays.cuh"
@@ -31,6 +30,18 @@ __global__ void selftest_log_kernel(unsigned lo, unsigned hi, unsigned long long
         const float2 b = log_exact2(make_float2(x, __uint_as_float((unsigned)(hi - (u - lo)))));
         bad += (__float_as_uint(a) != __float_as_uint(ref)) + (__float_as_uint(b.x) != __float_as_uint(ref));
         bad += (__float_as_uint(b.y) != __float_as_uint(logf(__uint_as_float((unsigned)(hi - (u - lo))))));
+    }
+    if (bad) atomicAdd(mism, bad);
+}
+// which 2: inputs whose lg2.approx.ftz differs from log2 (fp64) by more than tol (absolute) -- the bound the two-tier
+// sign logic of cadl_stream3.cuh and the threshold bands of phase A rest on
+__global__ void selftest_lg2_kernel(unsigned lo, unsigned hi, float tol, unsigned long long* mism) {
+    unsigned long long bad = 0;
+    for (unsigned long long u = (unsigned long long)lo + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; u <= hi;
+         u += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((unsigned)u);
+        const double err = fabs((double)lg2_approx(x) - log2((double)x));
+        bad += !(err <= (double)tol);
     }
     if (bad) atomicAdd(mism, bad);
 }
@@ -71,7 +82,6 @@ struct Ws {
     double* b_part() const { return reinterpret_cast<double*>(base + L.b_part); }
     double* img_sm() const { return reinterpret_cast<double*>(base + L.img_sm); }
     float* img_off() const { return reinterpret_cast<float*>(base + L.img_off); }
-    unsigned int* img_cnt() const { return reinterpret_cast<unsigned int*>(base + L.img_cnt); }
     ImgRec* img_rec() const { return reinterpret_cast<ImgRec*>(base + L.img_rec); }
     bool has_pyr() const { return L.pyr_blocks > 0; }
     PyrArrays pyr() const {
@@ -86,13 +96,17 @@ struct Ws {
     }
 };
 
-int g_force_generic = 0;
-int g_force_tile = 0;
-int g_no_coop = 0;          // bit 6: reprojection alone keeps the separate count kernel (no cooperative launch)
-int g_no_overlap = 0;       // bit 5: pooled-pyramid kernels in line on the caller's stream instead of beside phase A
-int g_old_stream = 0;      // bit 7: round-1 streaming kernel + finish kernel instead of stream2_kernel
+// Dispatch switches and per-launch timing exist only in the debug build (libcadl_dbg.so, -DCADL_DEBUG), which the
+// tests use to compare the kernels of one term set against each other; the product library has neither the entry
+// points nor the state.
+#ifdef CADL_DEBUG
+int g_force_generic = 0;    // bit 0: generic (any shape) phase-B kernel even for aligned shapes
+int g_force_no_tma = 0;     // bit 1 (with bit 3): tile kernel staged with cp.async instead of TMA
+int g_force_tile = 0;       // bit 3: the one-CTA-per-tile fast kernel instead of the streaming kernel
 int g_no_pdl = 0;           // bit 4: plain stream-ordered launches (no programmatic dependent launch)
-// cadl_debug_kernel_times: CUDA events between the launches of one cadl_stack_fwd_bwd call (debug / profiling aid)
+int g_no_overlap = 0;       // bit 5: pooled-pyramid kernels in line on the caller's stream instead of beside phase A
+int g_no_coop = 0;          // bit 6: reprojection alone keeps the separate count kernel (no cooperative launch)
+// cadl_debug_kernel_times: CUDA events between the launches of one cadl_stack_fwd_bwd call
 struct KTimes {
     bool on = false;
     int n = 0, n_last = 0;
@@ -118,10 +132,13 @@ void kt_finish() {
     }
     g_kt.n = 0;
 }
-unsigned long long* g_trace = nullptr;   // cadl_debug_set_trace
-int g_trace_cap = 0;       // bit 3: the one-CTA-per-tile fast kernel instead of the streaming split
-int g_force_no_tma = 0;
-int g_use_ws = 0;           // bit 2: warp-specialised persistent kernel instead of the plain one-tile-per-CTA fast kernel     // bit 1 of cadl_debug_force_generic: keep the fast kernel but stage with cp.async   // cadl_debug_force_generic(): tests compare the two phase-B kernels
+inline bool kt_on() { return g_kt.on; }
+#else
+constexpr int g_force_generic = 0, g_force_no_tma = 0, g_force_tile = 0, g_no_pdl = 0, g_no_overlap = 0, g_no_coop = 0;
+inline void kt_mark(cudaStream_t, const char*) {}
+inline void kt_finish() {}
+inline bool kt_on() { return false; }
+#endif
 
 WsLayout layout_for(int B, int H, int W) {
     WsLayout L = ws_layout(B, H, W);
@@ -234,26 +251,6 @@ cudaError_t launch_fast_m(PhaseBArgs& a, cudaStream_t st) {
         }
         a.use_tma = tm.ok ? 1 : 0;
     }
-    if constexpr ((F & FB_GRAD) != 0) {
-        if (a.use_tma && g_use_ws) {
-            // warp-specialised persistent form (opt-in: measured 198 us vs 194 us for the plain kernel at config 3 --
-            // both are bound by warps per SM, i.e. by the 128 registers of the full-resolution pass)
-            static bool ws_configured = false;
-            static int num_sms = 0;
-            if (!ws_configured) {
-                cudaError_t e = cudaFuncSetAttribute(phase_b_ws_kernel<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     (int)kWsSmemBytes);
-                if (e != cudaSuccess) return e;
-                int dev = 0;
-                cudaGetDevice(&dev);
-                cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-                ws_configured = true;
-            }
-            const int grid = a.b_rows < num_sms ? a.b_rows : num_sms;
-            phase_b_ws_kernel<F, M><<<grid, kWsThreads, kWsSmemBytes, st>>>(a, g_maps.pred, g_maps.gt);
-            return cudaGetLastError();
-        }
-    }
     phase_b_fast_kernel<F, M><<<a.b_rows, kThreadsB, kFastSmemBytes, st>>>(a, g_maps.pred, g_maps.gt);
     return cudaGetLastError();
 }
@@ -317,7 +314,7 @@ AuxStream* aux_for_current_device() {
 cudaError_t launch_pyramid(const PhaseBArgs& a, const Ws& ws, cudaStream_t st, int grid, bool pdl_pool, bool pdl) {
     const PyrArrays py = ws.pyr();
     cudaError_t e = launch_pdl(pyr_pool_kernel, dim3(grid), dim3(256), st, pdl_pool, a.pred, a.gt, a.B, a.H, a.W, a.eps_grad, py,
-                               ws.img_cnt());
+                               reinterpret_cast<unsigned int*>(ws.img_rec()));
     if (e != cudaSuccess) return e;
     kt_mark(st, "pyr_pool_kernel");
     PyrCoefArgs ca{};
@@ -331,75 +328,33 @@ cudaError_t launch_pyramid(const PhaseBArgs& a, const Ws& ws, cudaStream_t st, i
     return cudaSuccess;
 }
 
-// streaming split of the fast path: pooled pyramid -> coarse coefficients -> full-resolution pass (cadl_phase_b_stream.cuh)
+// streaming split of the fast path: pooled pyramid -> coarse coefficients (cadl_phase_b_stream.cuh) -> full-resolution pass
+// (cadl_stream3.cuh).  cudaErrorNotSupported: the caller takes the one-tile-per-CTA kernel instead.
 template <int F>
 cudaError_t launch_stream(PhaseBArgs& a, const Ws& ws, cudaStream_t st, bool* offset_done, const StepPlan& plan) {
     const PyrArrays py = ws.pyr();
     const int nblk = plan.pyr_grid > 0 ? plan.pyr_grid : ws.L.pyr_blocks;
     // (event records between the launches would serialise them anyway; after a cross-stream join the streaming
     //  kernel has two predecessors and is launched plainly)
-    const bool pdl = !g_no_pdl && !g_kt.on;
+    const bool pdl = !g_no_pdl && !kt_on();
     cudaError_t e = cudaSuccess;
+    if (!(a.eps_grad >= 1e-30f && (!(F & FB_SI) || a.eps_si == a.eps_grad) && (!(F & FB_RP) || a.eps_rp == a.eps_grad)))
+        return cudaErrorNotSupported;
     if (!plan.pyr_prelaunched) {
         e = launch_pyramid(a, ws, st, nblk, pdl, pdl);
         if (e != cudaSuccess) return e;
     }
-    if (!g_old_stream && !g_trace && a.eps_grad >= 1e-30f && (!(F & FB_SI) || a.eps_si == a.eps_grad) &&
-        (!(F & FB_RP) || a.eps_rp == a.eps_grad)) {
-        // round-2 kernel: TMA row ring, two-tier logs, packed reprojection, smoothness offset applied in-kernel
-        // (cadl_stream3.cuh)
-        Stream3Args s3{};
-        s3.c1 = py.c1; s3.nstrip = (a.W + 127) / 128;
-        s3.pyr_rows = a.b_part + (size_t)a.B * BF_COUNT; s3.n_pyr_rows = nblk;
-        s3.img = ws.img_rec(); s3.done = &ws.hdr()->ticket_b; s3.epoch = &ws.hdr()->pad[0];
-        if (!(F & FB_SMOOTH) || stream3_fill_smooth(a, s3)) {
-            e = launch_stream3(F, a, s3, st);
-            if (e == cudaSuccess) {
-                kt_mark(st, "stream3_kernel");
-                *offset_done = true;
-                return cudaSuccess;
-            }
-            if (e != cudaErrorNotSupported && e != cudaErrorCooperativeLaunchTooLarge) return e;
-            cudaGetLastError();
-        }
-    }
-    StreamArgs sa{};
-    sa.c1 = py.c1; sa.nstrip = (a.W + 127) / 128;
-    const int num_sms = num_sms_cached();
-    const int wave = kStreamCtasPerSm * num_sms * (kStreamThreads / 32);            // resident warps: 2 CTAs x 6 warps per SM (cadl_common.cuh)
-    const int SR = sa.nstrip * a.H;
-    sa.cpi = wave / a.B > 0 ? wave / a.B : 1;
-    if (sa.cpi > ws.L.stream_cpi) sa.cpi = ws.L.stream_cpi;         // workspace sized for this many rows per image
-    if (sa.cpi > SR) sa.cpi = SR;
-    sa.chunk_part = a.b_part + (size_t)(a.B + ws.L.pyr_blocks) * BF_COUNT;
-    sa.img_cnt = ws.img_cnt();
-    a.tiles_x = 1; a.tiles_y = 1;                    // finalize_results: one (already reduced) row per image
-    a.b_rows = a.B + nblk;
-    sa.trace = g_trace; sa.trace_cap = g_trace_cap;
-    const bool defer = (F & FB_SMOOTH) && a.grad;    // results + offset in stream_finish_kernel
-    sa.finalize_inline = defer ? 0 : 1;
-    int grid = (a.B * sa.cpi + kStreamThreads / 32 - 1) / (kStreamThreads / 32);
-    if (grid > kStreamCtasPerSm * num_sms) grid = kStreamCtasPerSm * num_sms;
-    const bool pdl_s = pdl && !plan.pyr_prelaunched;
-    if (a.mask) e = launch_pdl(phase_b_stream_kernel<F, true>, dim3(grid), dim3(kStreamThreads), st, pdl_s, a, sa);
-    else e = launch_pdl(phase_b_stream_kernel<F, false>, dim3(grid), dim3(kStreamThreads), st, pdl_s, a, sa);
+    // TMA row ring, two-tier logs, packed reprojection, smoothness offset applied in-kernel (cadl_stream3.cuh)
+    Stream3Args s3{};
+    s3.c1 = py.c1; s3.nstrip = (a.W + 127) / 128;
+    s3.pyr_rows = a.b_part + (size_t)a.B * BF_COUNT; s3.n_pyr_rows = nblk;
+    s3.img = ws.img_rec(); s3.done = &ws.hdr()->ticket_b; s3.epoch = &ws.hdr()->pad[0];
+    if ((F & FB_SMOOTH) && !stream3_fill_smooth(a, s3)) return cudaErrorNotSupported;
+    e = launch_stream3(F, a, s3, st);
     if (e != cudaSuccess) return e;
-    kt_mark(st, "phase_b_stream_kernel");
-    if (defer) {
-        const int HW = a.H * a.W;
-        const int vec = (HW % 4 == 0) && aligned(a.grad, 16);
-        int bx = (HW / 4 + 255) / 256;
-        // one resident wave: the kernel holds 3 CTAs of 256 threads per SM (us/step at config 3 by CTAs per image:
-        // 9 -> 196.1, 13 -> 190.5, 18 -> 194.7, 27 -> 191.6, 37 -> 192.0, 74 -> 193.5)
-        int cap = (3 * num_sms_cached()) / (a.B + 1);
-        if (bx > cap) bx = cap;
-        if (bx < 1) bx = 1;
-        e = launch_pdl(stream_finish_kernel, dim3(bx, a.B + 1), dim3(256), st, pdl, a, vec);
-        if (e != cudaSuccess) return e;
-        kt_mark(st, "stream_finish_kernel");
-        *offset_done = true;
-    }
-    return cudaGetLastError();
+    kt_mark(st, "stream3_kernel");
+    *offset_done = true;
+    return cudaSuccess;
 }
 
 template <int F>
@@ -415,7 +370,7 @@ cudaError_t launch_point_fast(PhaseBArgs& a, cudaStream_t st) {
     if (bpi < 1) bpi = 1;
     dim3 grid(bpi, a.B);
     a.b_rows = bpi * a.B;
-    const bool pdl = !g_no_pdl && !g_kt.on;
+    const bool pdl = !g_no_pdl && !kt_on();
     if (a.mask) return launch_pdl(phase_b_point_fast_kernel<F, true>, grid, dim3(kThreadsB), st, pdl, a);
     return launch_pdl(phase_b_point_fast_kernel<F, false>, grid, dim3(kThreadsB), st, pdl, a);
 }
@@ -613,13 +568,28 @@ int run_grad(const float* pred, const float* gt, const float* rgb, const float* 
     if (fast) {
         a.tiles_x = (W + FTW - 1) / FTW; a.tiles_y = (H + FTH - 1) / FTH;
         a.b_rows = a.tiles_x * a.tiles_y * B;
-        const bool stream = stream_path_ok(a, p, ws);
-        switch (t) {
-            case CADL_TERM_ALL: e = stream ? launch_stream<15>(a, ws, st, &offset_done, plan) : launch_fast<15>(a, st); break;
-            case CADL_TERM_SI | CADL_TERM_GRAD | CADL_TERM_SMOOTH: e = stream ? launch_stream<7>(a, ws, st, &offset_done, plan) : launch_fast<7>(a, st); break;
-            case CADL_TERM_GRAD: e = stream ? launch_stream<FB_GRAD>(a, ws, st, &offset_done, plan) : launch_fast<FB_GRAD>(a, st); break;
-            case CADL_TERM_SMOOTH: e = launch_fast<FB_SMOOTH>(a, st); break;
-            default: return CADL_ERR_UNSUPPORTED;
+        bool stream = stream_path_ok(a, p, ws);
+        if (stream) {
+            PhaseBArgs as = a;             // (launch_stream re-purposes the tile fields)
+            switch (t) {
+                case CADL_TERM_ALL: e = launch_stream<15>(as, ws, st, &offset_done, plan); break;
+                case CADL_TERM_SI | CADL_TERM_GRAD | CADL_TERM_SMOOTH: e = launch_stream<7>(as, ws, st, &offset_done, plan); break;
+                case CADL_TERM_GRAD: e = launch_stream<FB_GRAD>(as, ws, st, &offset_done, plan); break;
+                default: e = cudaErrorNotSupported; break;
+            }
+            if (e == cudaErrorNotSupported || e == cudaErrorCooperativeLaunchTooLarge) {
+                cudaGetLastError();
+                stream = false;            // e.g. unequal eps, a device without cooperative launch: the tile kernel
+            }
+        }
+        if (!stream) {
+            switch (t) {
+                case CADL_TERM_ALL: e = launch_fast<15>(a, st); break;
+                case CADL_TERM_SI | CADL_TERM_GRAD | CADL_TERM_SMOOTH: e = launch_fast<7>(a, st); break;
+                case CADL_TERM_GRAD: e = launch_fast<FB_GRAD>(a, st); break;
+                case CADL_TERM_SMOOTH: e = launch_fast<FB_SMOOTH>(a, st); break;
+                default: return CADL_ERR_UNSUPPORTED;
+            }
         }
     } else {
     a.b_rows = ws.L.b_tiles;
@@ -665,6 +635,7 @@ void cadl_default_params(cadl_params* p) {
 }
 
 int cadl_version(void) { return CADL_VERSION; }
+#ifdef CADL_DEBUG
 int cadl_debug_kernel_times(int enable, float* ms_out, const char** names_out, int cap) {
     g_kt.on = enable != 0;
     g_kt.n = 0;
@@ -676,15 +647,6 @@ int cadl_debug_kernel_times(int enable, float* ms_out, const char** names_out, i
     return n;
 }
 
-void cadl_debug_set_int(int key, int value) {
-    (void)key; (void)value;
-}
-
-void cadl_debug_set_trace(unsigned long long* dev_buf, int capacity_warps) {
-    g_trace = dev_buf;
-    g_trace_cap = dev_buf ? capacity_warps : 0;
-}
-
 void cadl_debug_force_generic(int on) {
     g_force_generic = on & 1;
     g_force_no_tma = (on >> 1) & 1;
@@ -692,9 +654,8 @@ void cadl_debug_force_generic(int on) {
     g_no_pdl = (on >> 4) & 1;
     g_no_overlap = (on >> 5) & 1;
     g_no_coop = (on >> 6) & 1;
-    g_old_stream = (on >> 7) & 1;
-    g_use_ws = (on >> 2) & 1;
 }
+#endif
 size_t cadl_sizeof_params(void) { return sizeof(cadl_params); }
 size_t cadl_sizeof_results(void) { return sizeof(cadl_results); }
 
@@ -809,7 +770,7 @@ int cadl_stack_fwd_bwd(const float* pred, const float* gt, const float* rgb, con
     // persistent CTA per SM; phase A follows on the caller's stream with a grid that leaves them room.
     StepPlan plan;
     AuxStream* aux = nullptr;
-    if (!g_no_overlap && !g_kt.on && phase_a_flags(*params) != 0 && results) {
+    if (!g_no_overlap && !kt_on() && phase_a_flags(*params) != 0 && results) {
         PhaseBArgs a;
         bool nothing = false;
         if (fill_b_args(a, pred, gt, rgb, K, mask, B, H, W, *params, grad_pred, results, ws, &nothing) == CADL_OK && !nothing &&
@@ -823,7 +784,7 @@ int cadl_stack_fwd_bwd(const float* pred, const float* gt, const float* rgb, con
     }
     // Reprojection alone, no metrics (BASELINE config 2): the gradient kernel counts the valid pixels itself
     if ((params->terms & CADL_TERM_ALL) == CADL_TERM_REPROJ && params->metrics == 0 && !g_force_generic && !g_no_coop &&
-        !g_kt.on && results) {
+        !kt_on() && results) {
         PhaseBArgs a;
         bool nothing = false;
         if (fill_b_args(a, pred, gt, rgb, K, mask, B, H, W, *params, grad_pred, results, ws, &nothing) == CADL_OK && !nothing &&
@@ -925,6 +886,8 @@ int cadl_selftest(int which, uint32_t lo_bits, uint32_t hi_bits, float param, un
     else if (which == 1) {
         if (!markstein_safe_host(param)) return CADL_ERR_UNSUPPORTED;
         selftest_div_kernel<<<148 * 8, 256, 0, st>>>(lo_bits, hi_bits, param, mismatches_dev);
+    } else if (which == 2) {
+        selftest_lg2_kernel<<<148 * 8, 256, 0, st>>>(lo_bits, hi_bits, param, mismatches_dev);
     } else return CADL_ERR_UNSUPPORTED;
     return cuda_rc(cudaGetLastError());
 }

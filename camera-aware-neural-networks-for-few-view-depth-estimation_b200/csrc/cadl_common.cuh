@@ -52,27 +52,13 @@ struct WsHeader {
 };
 
 struct WsLayout {
-    size_t header, stats, img_psum, a_part, b_part, img_sm, img_off, img_cnt, img_rec, total;
+    size_t header, stats, img_psum, a_part, b_part, img_sm, img_off, img_rec, total;
     size_t pyr_lp[3], pyr_lg[3], pyr_rq[3], pyr_c1;   // streaming fast path (cadl_phase_b_stream.cuh); 0 = absent
     int a_blocks_per_img, a_blocks, b_tiles;
-    int stream_cpi;   // streaming kernel: static shares per image (one per warp of the resident wave)
     int pyr_blocks;   // CTAs of pyr_pool_kernel / pyr_coef_kernel (0: shape not a multiple of 8)
 };
 
-// CTA shape of phase_b_stream_kernel.  Unconstrained the kernel wants 167 registers; 2 x 192 threads per SM give it
-// that (12 warps/SM, no spills, nothing re-materialised per row).  Measured us/step at config 3: 2 x 192 -> 192.0,
-// 3 x 128 -> 192.8, 4 x 96 -> 192.5, 2 x 256 (128 registers, 16 warps) -> 195.6, 2 x 160 -> 211.0,
-// 2 x 320 (96 registers, spills) -> 222.9, 2 x 384 -> 232.1.
-#ifndef CADL_STREAM_THREADS
-#define CADL_STREAM_THREADS 192
-#endif
-#ifndef CADL_STREAM_MINB
-#define CADL_STREAM_MINB 2
-#endif
-constexpr int kStreamCtasPerSm = CADL_STREAM_MINB;
-constexpr int kStreamThreads = CADL_STREAM_THREADS;   // threads per CTA of phase_b_stream_kernel (2 CTAs per SM)
 constexpr int kPointBlocks = 148 * 8;       // partial rows of the pointwise kernels
-constexpr int kStreamWaveWarps = 160 * CADL_STREAM_MINB * (CADL_STREAM_THREADS / 32);  // upper bound of the streaming kernel's resident warps (CTAs per SM x warps per CTA x <=160 SMs)
 
 constexpr int kThreadsA = 256;
 constexpr int kThreadsB = 256;
@@ -104,18 +90,15 @@ __host__ inline WsLayout ws_layout(int B, int H, int W) {
     L.stats = o;    o = align_up(o + sizeof(double) * ST_COUNT, 256);
     L.img_psum = o; o = align_up(o + sizeof(double) * B, 256);
     L.a_part = o;   o = align_up(o + sizeof(double) * (size_t)L.a_blocks * AF_COUNT, 256);
-    L.stream_cpi = kStreamWaveWarps / B > 0 ? kStreamWaveWarps / B : 1;
     const bool pyr = (H % 8 == 0) && (W % 8 == 0);
     L.pyr_blocks = pyr ? (int)(((size_t)B * (H / 8) * (W / 8) + 255) / 256) : 0;
     size_t b_rows = (size_t)L.b_tiles;
     if (b_rows < (size_t)kPointBlocks) b_rows = kPointBlocks;
-    // streaming path: [B per-image rows][pyr_coef_kernel rows][one row per chunk]
-    if (pyr && b_rows < (size_t)B + L.pyr_blocks + (size_t)B * L.stream_cpi)
-        b_rows = (size_t)B + L.pyr_blocks + (size_t)B * L.stream_cpi;
+    // streaming path: [B per-image rows (unused since round 2)][pyr_coef_kernel rows]
+    if (pyr && b_rows < (size_t)B + L.pyr_blocks) b_rows = (size_t)B + L.pyr_blocks;
     L.b_part = o;   o = align_up(o + sizeof(double) * b_rows * BF_COUNT, 256);
     L.img_sm = o;   o = align_up(o + sizeof(double) * (size_t)B * 2, 256);
     L.img_off = o;  o = align_up(o + sizeof(float) * (size_t)B, 256);
-    L.img_cnt = o;  o = align_up(o + sizeof(unsigned int) * (size_t)B, 256);   // chunks done per image (streaming kernel)
     L.img_rec = o;  o = align_up(o + 128 * (size_t)B, 256);                    // ImgRec per image (cadl_stream3_host.h)
     for (int s = 0; s < 3; ++s) {
         const size_t cells = pyr ? (size_t)B * (H >> (s + 1)) * (W >> (s + 1)) : 0;

@@ -31,9 +31,10 @@
 namespace cadl {
 
 // Edge residuals (log2 units) below this magnitude take the exact tier.  Bound of |e_approx * ln2 - e_reference|:
-// four lg2.approx results (measured abs error < 2^-21 incl. the rounding of the result for |lg2| < 32), three fp32
-// subtractions of magnitude < 64 (3 x 2^-19), and on the reference side four logf (1 ulp of <= 13.9: 2^-20 each) plus
-// three subtractions: < 1.9e-5 in total; 2^-15 = 3.05e-5 leaves 60 % margin.
+// approximate side: four lg2.approx results (absolute error < 1.25e-6 incl. the rounding of a result of
+// magnitude < 32: measured by cadl_selftest(2), tests/test_math_gpu.py) and three fp32 subtractions of magnitude < 32
+// (3 x 2^-20): 7.9e-6 in log2 units = 5.5e-6; reference side: four logf (1 ulp of <= 13.9: 2^-20 each) and three
+// subtractions: 6.7e-6.  Together 1.22e-5 = 1.76e-5 in log2 units; 2^-15 = 3.05e-5 leaves 40 % margin.
 constexpr float kBand = 3.0517578125e-05f;
 constexpr float kLn2 = 0.693147180559945309f;
 

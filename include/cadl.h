@@ -96,28 +96,24 @@ int cadl_version(void);
 size_t cadl_sizeof_params(void);
 size_t cadl_sizeof_results(void);
 const char* cadl_error_string(int code);
-/* Test hook (bit mask): 1 = always take the generic phase-B kernel (any shape/alignment) instead of the
- * aligned fast path; 8 = fast path as ONE tile kernel (cadl_phase_b_fast.cuh) instead of the streaming split
- * (cadl_phase_b_stream.cuh); together with 8: 2 = stage tiles with cp.async instead of TMA, 4 = warp-specialised
- * persistent tile kernel (cadl_phase_b_ws.cuh); 16 = no programmatic dependent launch; 32 = the pooled-pyramid
- * kernels in line on the caller's stream instead of beside phase A on the auxiliary stream; 64 = reprojection alone
- * with the separate count kernel instead of the single cooperative launch.  All variants must
- * produce the same values.  Process-global; not for production use. */
+#ifdef CADL_DEBUG
+/* Debug build only (libcadl_dbg.so; the product library exports neither).
+ * cadl_debug_force_generic, bit mask: 1 = always take the generic phase-B kernel (any shape/alignment) instead of the
+ * aligned fast path; 8 = fast path as ONE tile kernel (cadl_phase_b_fast.cuh) instead of the pyramid + streaming
+ * kernels; together with 8: 2 = stage tiles with cp.async instead of TMA; 16 = no programmatic dependent launch;
+ * 32 = the pooled-pyramid kernels in line on the caller's stream instead of beside phase A on the auxiliary stream;
+ * 64 = reprojection alone with the separate count kernel instead of the single cooperative launch.  All variants must
+ * produce the same values (tests/test_math_gpu.py).  Process-global.
+ * cadl_debug_kernel_times: with enable != 0 every following cadl_stack_fwd_bwd call records a CUDA event after each of
+ * its launches and SYNCHRONISES at the end.  Returns the number of intervals of the LAST timed call and copies up to
+ * cap of them: ms_out[i] = milliseconds up to the end of the launch names_out[i] (static strings). */
 void cadl_debug_force_generic(int on);
-/* Tuning hook: key 0 = images per group of the streaming gradient kernel (default 8).  Process-global. */
-void cadl_debug_set_int(int key, int value);
-/* Debug trace of the streaming phase-B kernel: while dev_buf is non-NULL every warp (global index < capacity_warps)
- * writes {SM id, start globaltimer ns, end globaltimer ns, work items processed} as 4 x uint64 at dev_buf[4*warp].
- * NULL switches it off.  Process-global; profiling aid (profiles/trace_stream.py), not for production use. */
-void cadl_debug_set_trace(unsigned long long* dev_buf, int capacity_warps);
-/* Debug timing: with enable != 0 every following cadl_stack_fwd_bwd call records a CUDA event after each of its
- * launches and SYNCHRONISES at the end.  Returns the number of intervals of the LAST timed call and copies up to
- * cap of them: ms_out[i] = milliseconds up to the end of the launch names_out[i] (static strings; the last
- * interval, "end", is whatever follows the last named kernel).  Process-global; profiling aid only. */
 int cadl_debug_kernel_times(int enable, float* ms_out, const char** names_out, int cap);
+#endif
 /* Test hook: counts (into *mismatches_dev, a device uint64 the caller zeroed) the inputs with bit pattern in
  * [lo_bits, hi_bits] for which a device-math replica differs from the CUDA library form.
- *   which 0: log replica (scalar and packed fp32x2) vs logf;  which 1: Markstein a/param vs IEEE division. */
+ *   which 0: log replica (scalar and packed fp32x2) vs logf;  which 1: Markstein a/param vs IEEE division;
+ *   which 2: lg2.approx.ftz vs log2 in fp64: counts the inputs whose absolute error exceeds `param`. */
 int cadl_selftest(int which, uint32_t lo_bits, uint32_t hi_bits, float param, unsigned long long* mismatches_dev,
                   cadl_stream_t stream);
 

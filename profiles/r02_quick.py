@@ -50,13 +50,11 @@ for metrics in (3, 0):
           f"loss {r_new['loss_total']:.9f} vs {r_old['loss_total']:.9f}; "
           + " ".join(f"{k}={r_new[k]:.8f}/{r_old[k]:.8f}" for k in ("si_loss", "grad_loss", "smooth_loss", "reproj_loss")))
     for gsz in [8]:
-        pkg.lib().cadl_debug_set_int(0, gsz)
         t_new = timeit(params)
         pkg.force_generic(128)
         t_old = timeit(params)
         pkg.force_generic(0)
         print(f"[{tag}] metrics={metrics} gsz={gsz}: new {t_new:7.1f} us/step   old {t_old:7.1f} us/step")
-    pkg.lib().cadl_debug_set_int(0, 8)
     pkg.kernel_times(True)
     for _ in range(3):
         step(params)

@@ -11,10 +11,13 @@ import torch
 from conftest import ROOT
 
 
-def _declared_symbols():
+def _declared_symbols(debug=False):
     txt = open(os.path.join(ROOT, "include", "cadl.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(cadl_[a-zA-Z0-9_]+)\s*\(", txt)))
+    dbg = "".join(re.findall(r"#ifdef CADL_DEBUG(.*?)#endif", txt, flags=re.S))
+    txt = re.sub(r"#ifdef CADL_DEBUG.*?#endif", "", txt, flags=re.S)
+    find = lambda t: sorted(set(re.findall(r"\b(cadl_[a-zA-Z0-9_]+)\s*\(", t)))
+    return (find(dbg), find(txt)) if debug else find(txt)
 
 
 def test_library_exports_every_declared_symbol(pkg):
@@ -24,6 +27,19 @@ def test_library_exports_every_declared_symbol(pkg):
     for n in names:
         assert hasattr(L, n), f"libcadl.so does not export {n}"
     assert set(names) == set(pkg.ABI_SYMBOLS)
+
+
+def test_debug_hooks_live_in_the_debug_library_only(pkg):
+    """Dispatch switches and per-launch timing are compiled out of the product library (-DCADL_DEBUG builds
+    libcadl_dbg.so, which the kernel-vs-kernel tests select through pkg.force_generic)."""
+    dbg_names, names = _declared_symbols(debug=True)
+    assert dbg_names == ["cadl_debug_force_generic", "cadl_debug_kernel_times"]
+    L, D = pkg.lib(), pkg.debug_lib()
+    for n in dbg_names:
+        assert not hasattr(L, n), f"product library exports {n}"
+        assert hasattr(D, n)
+    for n in names:
+        assert hasattr(D, n)
 
 
 def test_struct_mirrors(pkg):

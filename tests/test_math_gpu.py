@@ -21,6 +21,17 @@ def test_log_replica_is_bit_identical_to_logf_over_the_whole_clamped_range(pkg):
     assert pkg.selftest(0, _bits(1e-7), _bits(1100.0)) == 0
 
 
+def test_lg2_approx_error_bound_behind_the_two_tier_signs(pkg):
+    """lg2.approx.ftz over every float the clamps can produce.  Absolute error incl. the fp32 rounding of the result:
+    below 1.25e-6 everywhere (|log2 x| < 32: half an ulp of the result alone is 2^-20 = 0.95e-6) and below 1e-6
+    where |log2 x| < 16.  The guard band kBand = 2^-15 of cadl_stream3.cuh (four such logs and three
+    subtractions, plus the reference's own four logf and three subtractions: 1.7e-5 in log2 units) and the
+    delta-threshold bands of phase A are derived from these figures."""
+    assert pkg.selftest(2, _bits(1e-7), _bits(1100.0), 1.25e-6) == 0
+    assert pkg.selftest(2, _bits(2.0 ** -16), _bits(1100.0), 1.0e-6) == 0
+    assert pkg.selftest(2, _bits(1e-7), _bits(1100.0), 2.0 ** -24) > 0          # (the check can fail)
+
+
 @pytest.mark.parametrize("b", [518.8579, 519.4696, 259.43, 1037.7158, 0.3333, 3.0, 7919.0, 1e-3])
 def test_markstein_division_is_correctly_rounded(pkg, b):
     """a / (fx + eps) with a = (u - cx) * depth spanning 1e-4 .. 1e5 in both signs, vs __fdiv_rn."""
@@ -42,9 +53,9 @@ def test_fast_kernel_equals_generic_kernel(pkg, shape, terms):
             "smooth": T.TERM_SMOOTH}[terms]
     over = {"grad": dict(w_grad=1.0), "smooth": dict(w_smooth=1.0)}.get(terms, {})
     res = []
-    # 0: default (streaming split where it applies); 1: generic kernel; 8: tile fast kernel (TMA staging);
-    # 10: tile fast kernel, cp.async staging; 12: warp-specialised persistent tile kernel
-    for generic in (8, 1, 10, 12, 0):
+    # 0: default = the product library (pyramid + streaming kernels where they apply); through the debug library:
+    # 1: generic kernel; 8: tile fast kernel (TMA staging); 10: tile fast kernel, cp.async staging
+    for generic in (8, 1, 10, 0):
         pkg.force_generic(generic)
         try:
             ws = pkg.stack_fwd_bwd(b["pred"], b["gt"], b["rgb"], b["K"] if bits & T.TERM_REPROJ else None, None,
@@ -53,8 +64,7 @@ def test_fast_kernel_equals_generic_kernel(pkg, shape, terms):
             res.append((pkg.results_dict(ws.read_results()), ws.grad.clone()))
         finally:
             pkg.force_generic(False)
-    (rf, gf), (rg, gg), (rc, gc), (rt, gt_), (rs, gs) = res
-    assert torch.equal(gf, gt_)                            # plain fast kernel == warp-specialised, bit for bit
+    (rf, gf), (rg, gg), (rc, gc), (rs, gs) = res
     # streaming kernel vs tile kernel: same signs; the pointwise terms use approximate logs there (1e-6, a tenth of the parity bar)
     assert float((gs - gf).abs().max()) <= 1e-6 * float(gf.abs().max()), float((gs - gf).abs().max())
     for k in ("loss_total", "si_loss", "grad_loss", "smooth_loss", "reproj_loss"):

@@ -65,6 +65,13 @@ inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_
 
 thread_local char g_err_detail[256];
 
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+    return dev;
+}
+
 inline bool markstein_safe_host(float b) {
     uint32_t u;
     memcpy(&u, &b, 4);
@@ -185,12 +192,14 @@ cudaError_t dispatch_a(uint32_t f, const PhaseAArgs& a, dim3 grid, cudaStream_t 
 
 template <int F>
 cudaError_t launch_tile(const PhaseBArgs& a, cudaStream_t st) {
-    static bool configured = false;   // per-process; attribute is per-function, idempotent
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};   // the attribute applies to the current device only
+    const int dev = current_device();
+    if (dev < 0) return cudaErrorInvalidDevice;
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(phase_b_tile_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)kTileSmemBytes);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev] = true;
     }
     phase_b_tile_kernel<F><<<a.b_rows, kThreadsB, kTileSmemBytes, st>>>(a);
     return cudaGetLastError();
@@ -235,12 +244,14 @@ thread_local TileMaps g_maps;   // re-encoded only when a pointer or the shape c
 
 template <int F, bool M>
 cudaError_t launch_fast_m(PhaseBArgs& a, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};
+    const int dev = current_device();
+    if (dev < 0) return cudaErrorInvalidDevice;
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(phase_b_fast_kernel<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)kFastSmemBytes);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev] = true;
     }
     a.use_tma = 0;
     if ((F & FB_GRAD) && !g_force_no_tma) {
@@ -272,14 +283,12 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStre
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-int num_sms_cached() {
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return num_sms;
+int num_sms_cached() {         // of the CURRENT device (a process may drive several)
+    static int num_sms[kMaxDevices] = {};
+    const int dev = current_device();
+    if (dev < 0) return 1;
+    if (!num_sms[dev]) cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    return num_sms[dev] > 0 ? num_sms[dev] : 1;
 }
 
 // How one cadl_stack_fwd_bwd call is laid out over launches (decided once, used by the reduce and the gradient part).
@@ -378,12 +387,8 @@ cudaError_t launch_point_fast(PhaseBArgs& a, cudaStream_t st) {
 // Reprojection alone, no metrics: count + gradient in ONE cooperative launch (phase_b_point_fast_kernel<.., COUNT>).
 // Returns cudaErrorNotSupported when the grid cannot be co-resident, so the caller takes the two-launch path.
 cudaError_t launch_point_count(PhaseBArgs& a, cudaStream_t st) {
-    static int coop = -1;
-    if (coop < 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    }
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, current_device() < 0 ? 0 : current_device());
     if (!coop) return cudaErrorNotSupported;
     const int wpb = kThreadsB / 32;
     int bpi = (4 * num_sms_cached()) / a.B;
@@ -949,7 +954,7 @@ int cadl_p2p_close(void* inbox_dev, int own) {
 }
 
 int cadl_stats_exchange(void* workspace, void* const* inboxes_host, int rank, int world, unsigned long long epoch,
-                        cadl_stream_t stream) {
+                        double timeout_s, cadl_stream_t stream) {
     if (!workspace || !inboxes_host) return CADL_ERR_NULL;
     if (world < 1 || world > kP2PMaxWorld || rank < 0 || rank >= world || epoch == 0) return CADL_ERR_SHAPE;
     P2PArgs a{};
@@ -959,15 +964,18 @@ int cadl_stats_exchange(void* workspace, void* const* inboxes_host, int rank, in
         a.inbox[r] = static_cast<double*>(inboxes_host[r]);
     }
     a.rank = rank; a.world = world; a.epoch = epoch;
+    a.timeout_ns = (unsigned long long)((timeout_s > 0.0 ? timeout_s : 600.0) * 1e9);
     a.error = reinterpret_cast<int*>(a.inbox[rank] + 2 * (size_t)world * kP2PSlotDoubles);
     stats_exchange_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(a);
     return cuda_rc(cudaGetLastError());
 }
 
-int cadl_p2p_error(const void* own_inbox_dev, int world, int* error_host) {
+int cadl_p2p_error(void* own_inbox_dev, int world, int* error_host, int clear) {
     if (!own_inbox_dev || !error_host) return CADL_ERR_NULL;
-    const char* p = static_cast<const char*>(own_inbox_dev) + sizeof(double) * 2 * (size_t)world * kP2PSlotDoubles;
-    return cuda_rc(cudaMemcpy(error_host, p, sizeof(int), cudaMemcpyDeviceToHost));
+    char* p = static_cast<char*>(own_inbox_dev) + sizeof(double) * 2 * (size_t)world * kP2PSlotDoubles;
+    cudaError_t e = cudaMemcpy(error_host, p, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && clear && *error_host) e = cudaMemset(p, 0, sizeof(int));
+    return cuda_rc(e);
 }
 
 int cadl_accumulate(const float* values_dev, int n, double weight, double* acc_dev, cadl_stream_t stream) {

@@ -43,7 +43,15 @@ __global__ void __launch_bounds__(256) batch_prep_kernel(const PrepArgs a) {
     float contrast = 1.f, brightness = 1.f;
     if constexpr (AUG) {
         const float* g = a.aug + (size_t)b * 8;
-        if (__ldg(g + 2) > 0.f) { cx0 = (int)__ldg(g + 0); cy0 = (int)__ldg(g + 1); cw = (int)__ldg(g + 2); ch = (int)__ldg(g + 3); }
+        if (__ldg(g + 2) > 0.f) {
+            cx0 = (int)__ldg(g + 0); cy0 = (int)__ldg(g + 1); cw = (int)__ldg(g + 2); ch = (int)__ldg(g + 3);
+            // the reference's Slice clamps the window to the tensor (sunrgbd_loader.cpp:395-397): an overshooting
+            // window (crop_x can be 1 with crop_w == w at scale 1.0) must not read out of bounds
+            cx0 = cx0 < 0 ? 0 : (cx0 > a.w - 1 ? a.w - 1 : cx0);
+            cy0 = cy0 < 0 ? 0 : (cy0 > a.h - 1 ? a.h - 1 : cy0);
+            cw = cw > a.w - cx0 ? a.w - cx0 : cw;
+            ch = ch < 1 ? 1 : (ch > a.h - cy0 ? a.h - cy0 : ch);
+        }
         flip = __ldg(g + 4) != 0.f;
         jitter = __ldg(g + 5) != 0.f;
         contrast = __ldg(g + 6);
@@ -214,7 +222,9 @@ __global__ void __launch_bounds__(256) gradscale_kernel(const ClipArgs a) {
 //   2. waits until all `world` flags of its OWN inbox carry this epoch;
 //   3. sums the slots in rank order (fixed order: every rank computes bit-identical sums) into its statistics vector.
 // Two parities suffice: nobody can start epoch e+1 before it has read epoch e, and epoch e+2 needs everybody's e+1.
-// The wait is bounded (~2 s of globaltimer): on timeout the kernel flags an error instead of hanging the GPU.
+// The wait is bounded (timeout_ns of globaltimer, chosen by the caller: rank skew of seconds is routine in training --
+// checkpointing, validation, loader stalls): on timeout the kernel does not hang the GPU; it sets a sticky error flag
+// and writes NaN into the statistics, so the step's loss and gradient are visibly invalid instead of silently wrong.
 // ------------------------------------------------------------------------------------------------
 constexpr int kP2PSlotDoubles = ST_COUNT + 2;     // 32 values, flag, pad
 constexpr int kP2PMaxWorld = 16;
@@ -224,11 +234,14 @@ struct P2PArgs {
     double* inbox[kP2PMaxWorld];        // inbox[r]: rank r's inbox as mapped in THIS process (inbox[rank] = own)
     int rank, world;
     unsigned long long epoch;           // > 0, the same on every rank, incremented per exchange
-    int* error;                         // set to 1 on timeout
+    int* error;                         // set to 1 on timeout (sticky until cadl_p2p_error clears it)
+    unsigned long long timeout_ns;
 };
 
 __global__ void __launch_bounds__(64) stats_exchange_kernel(const P2PArgs a) {
+    __shared__ int s_timeout;
     const int t = threadIdx.x;
+    if (t == 0) s_timeout = 0;
     const size_t slot = ((size_t)(a.epoch & 1ull) * a.world + a.rank) * kP2PSlotDoubles;
     if (t < ST_COUNT) {
         const double v = a.stats[t];
@@ -248,7 +261,7 @@ __global__ void __launch_bounds__(64) stats_exchange_kernel(const P2PArgs a) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
             if (seen == a.epoch) break;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (now - t0 > 2000000000ull) { *a.error = 1; break; }
+            if (now - t0 > a.timeout_ns) { *a.error = 1; s_timeout = 1; break; }
             __nanosleep(200);
         }
     }
@@ -257,7 +270,7 @@ __global__ void __launch_bounds__(64) stats_exchange_kernel(const P2PArgs a) {
         double sum = 0.0;
         for (int r = 0; r < a.world; ++r)
             sum += reinterpret_cast<const volatile double*>(a.inbox[a.rank] + ((size_t)(a.epoch & 1ull) * a.world + r) * kP2PSlotDoubles)[t];
-        a.stats[t] = sum;
+        a.stats[t] = s_timeout ? __longlong_as_double(0x7ff8000000000000ll) : sum;      // a stale slot must not pass as a statistic
     }
 }
 

@@ -44,8 +44,9 @@ class P2PStatsExchange:
     Setup (once): every rank allocates its inbox and the 64-byte CUDA IPC handles are all-gathered through
     torch.distributed; per step: ``exchange(ws)`` between stack_reduce and stack_grad, on the current stream."""
 
-    def __init__(self, pkg, device: torch.device, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, pkg, device: torch.device, group: Optional[dist.ProcessGroup] = None, timeout_s: float = 600.0):
         import ctypes as C
+        self.timeout_s = float(timeout_s)
         self.pkg, self.C, self.L = pkg, C, pkg.lib()
         self.device = device
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -55,8 +56,8 @@ class P2PStatsExchange:
         L.cadl_p2p_alloc.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_char_p]
         L.cadl_p2p_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
         L.cadl_p2p_close.argtypes = [C.c_void_p, C.c_int]
-        L.cadl_stats_exchange.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_ulonglong, C.c_void_p]
-        L.cadl_p2p_error.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.cadl_stats_exchange.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_ulonglong, C.c_double, C.c_void_p]
+        L.cadl_p2p_error.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int]
         with torch.cuda.device(device):
             own = C.c_void_p()
             handle = C.create_string_buffer(64)
@@ -86,14 +87,22 @@ class P2PStatsExchange:
         self.epoch += 1
         with torch.cuda.device(self.device):
             rc = self.L.cadl_stats_exchange(self.pkg._ptr(ws.buf), self.ptrs, self.rank, self.world, self.epoch,
+                                            self.timeout_s,
                                             self.C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
         self.pkg._check(rc, "cadl_stats_exchange")
 
-    def timed_out(self) -> bool:
+    def timed_out(self, clear: bool = False) -> bool:
         e = self.C.c_int(0)
         with torch.cuda.device(self.device):
-            self.pkg._check(self.L.cadl_p2p_error(self.own, self.world, self.C.byref(e)), "cadl_p2p_error")
+            self.pkg._check(self.L.cadl_p2p_error(self.own, self.world, self.C.byref(e), int(clear)), "cadl_p2p_error")
         return e.value != 0
+
+    def check(self) -> None:
+        """Call where the step's results are read on the host (a sync point anyway): a rank that waited longer than
+        timeout_s for a peer has NaN statistics for that step; say so instead of training on.  Clears the flag."""
+        if self.timed_out(clear=True):
+            raise RuntimeError(f"cadl: rank {self.rank} waited more than {self.timeout_s:g} s for a peer's loss statistics "
+                               "(cadl_stats_exchange); this step's loss and gradient are NaN")
 
     def close(self) -> None:
         with torch.cuda.device(self.device):
@@ -112,15 +121,15 @@ def si_from_stats(stats: torch.Tensor, lam: float = 0.5) -> float:
 
 def combine_shares(local: Dict[str, float], weights=(1.0, 0.1, 0.001, 0.01),
                    group: Optional[dist.ProcessGroup] = None, device="cpu") -> Dict[str, float]:
-    """In mode "global" the SI and reprojection losses a rank reports are already global, while the
-    gradient-matching and smoothness losses are this rank's additive share (their denominators use the
-    global batch size).  Sum the shares and rebuild the weighted total (depth_loss.h:427-430)."""
-    t = torch.tensor([local["d_grad"], local["d_smooth"], local.get("reproj_sum_e", 0.0)], dtype=torch.float64,
-                     device=device)
+    """In mode "global" the SI loss a rank reports is already global (it is a function of the exchanged statistics),
+    while the gradient-matching, smoothness and reprojection losses are this rank's additive share (local sums over
+    global denominators: B_global * H * W edges, n_global valid pixels).  Sum the shares and rebuild the weighted total
+    (depth_loss.h:427-430)."""
+    t = torch.tensor([local["d_grad"], local["d_smooth"], local["d_reproj"]], dtype=torch.float64, device=device)
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     out = dict(local)
-    out["d_grad"], out["d_smooth"] = float(t[0]), float(t[1])
+    out["d_grad"], out["d_smooth"], out["d_reproj"] = float(t[0]), float(t[1]), float(t[2])
     w = weights
     out["d_total"] = w[0] * out["d_si"] + w[1] * out["d_grad"] + w[2] * out["d_smooth"] + w[3] * out["d_reproj"]
     return out

@@ -221,17 +221,19 @@ int cadl_batch_augment(const float* rgb_in, const float* depth_in, const float* 
  * an inbox (cadl_p2p_alloc: cudaMalloc + CUDA IPC handle), maps every peer's (cadl_p2p_open on the 64-byte handles
  * the ranks all-gather once, with any transport), and calls cadl_stats_exchange between cadl_stack_reduce and
  * cadl_stack_grad with an epoch counter that is the same on every rank and grows by one per call (start at 1).
- * The kernel pushes this rank's vector into every inbox, waits (bounded, ~2 s) for the others, and sums in rank
+ * The kernel pushes this rank's vector into every inbox, waits for the others (at most timeout_s seconds of device
+ * time; <= 0 selects 600 s: rank skew of seconds is routine -- checkpointing, validation, loader stalls), and sums in rank
  * order -- the result is bit-identical on all ranks.  inboxes_host[r] = rank r's inbox as mapped in this process
- * (inboxes_host[rank] = the pointer cadl_p2p_alloc returned).  world <= 16, one node.  cadl_p2p_error reads the
- * timeout flag (synchronises). */
+ * (inboxes_host[rank] = the pointer cadl_p2p_alloc returned).  world <= 16, one node.  On a timeout the statistics
+ * become NaN (the step's loss and gradient are then visibly invalid, never silently wrong) and a sticky flag is set:
+ * cadl_p2p_error reads it (synchronises) and, with clear != 0, resets it. */
 size_t cadl_p2p_inbox_bytes(int world);
 int cadl_p2p_alloc(int world, void** inbox_dev, unsigned char handle_out[64]);
 int cadl_p2p_open(const unsigned char handle[64], void** inbox_dev);
 int cadl_p2p_close(void* inbox_dev, int own);
 int cadl_stats_exchange(void* workspace, void* const* inboxes_host, int rank, int world, unsigned long long epoch,
-                        cadl_stream_t stream);
-int cadl_p2p_error(const void* own_inbox_dev, int world, int* error_host);
+                        double timeout_s, cadl_stream_t stream);
+int cadl_p2p_error(void* own_inbox_dev, int world, int* error_host, int clear);
 
 /* Device-resident running sums of per-batch scalars: acc_dev[i] += weight * values_dev[i] for i < n and
  * acc_dev[n] += weight (acc_dev: n + 1 doubles the caller zeroed).  Replaces the trainers'

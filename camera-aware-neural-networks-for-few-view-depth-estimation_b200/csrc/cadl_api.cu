@@ -453,8 +453,8 @@ int run_reduce(const float* pred, const float* gt, const uint8_t* mask, int B, i
                (!mask || aligned(mask, 4));
     a.eps_si = p.eps_si; a.eps_rp = p.eps_reproj; a.min_d = p.min_depth; a.max_d = p.max_depth;
     {
-        // guard bands of the delta thresholds in the log2 domain: two lg2.approx (2^-22 absolute each), the fp32
-        // rounding of their results and of the difference (ulp of the largest |log2 depth| in range)
+        // guard bands of the delta thresholds in the log2 domain: two lg2.approx (about one ulp of the result each:
+        // < 6.8e-7 for depths in [0.05, 20], growing with |log2 depth|) and the fp32 rounding of the difference
         float big = fabsf(log2f(p.max_depth > 0.f ? p.max_depth : 1.f));
         const float lo = fabsf(log2f(p.min_depth > 1e-30f ? p.min_depth : 1e-30f));
         if (lo > big) big = lo;

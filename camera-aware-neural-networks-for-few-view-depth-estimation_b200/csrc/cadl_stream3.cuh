@@ -31,10 +31,11 @@
 namespace cadl {
 
 // Edge residuals (log2 units) below this magnitude take the exact tier.  Bound of |e_approx * ln2 - e_reference|:
-// approximate side: four lg2.approx results (absolute error < 1.25e-6 incl. the rounding of a result of
-// magnitude < 32: measured by cadl_selftest(2), tests/test_math_gpu.py) and three fp32 subtractions of magnitude < 32
-// (3 x 2^-20): 7.9e-6 in log2 units = 5.5e-6; reference side: four logf (1 ulp of <= 13.9: 2^-20 each) and three
-// subtractions: 6.7e-6.  Together 1.22e-5 = 1.76e-5 in log2 units; 2^-15 = 3.05e-5 leaves 40 % margin.
+// approximate side: four lg2.approx results (absolute error < 2.3e-6 incl. the rounding of a result of magnitude < 20:
+// measured by cadl_selftest(2), tests/test_math_gpu.py, profiles/lg2_probe.py) and three fp32 subtractions of
+// magnitude < 32 (3 x 2^-20): 1.2e-5 in log2 units = 8.3e-6; reference side: four logf (1 ulp of <= 13.9: 2^-20 each)
+// and three subtractions: 6.7e-6.  Together 1.5e-5 = 2.16e-5 in log2 units; 2^-15 = 3.05e-5 leaves 29 % margin (and the
+// worst case needs all four values near the lower clamp, where equal inputs give equal logs and cancel).
 constexpr float kBand = 3.0517578125e-05f;
 constexpr float kLn2 = 0.693147180559945309f;
 

@@ -248,6 +248,52 @@ def test_metrics_fused_equals_standalone_and_oracle(pkg, oracle):
         assert rel_err(r["train"][k], tr[k]) <= TOL, k
 
 
+def test_metrics_with_depths_outside_the_eval_range(pkg, oracle):
+    """pred and gt planted outside [0.1, 10] (and pred far inside gt's valid range): DepthMetrics::compute clamps pred
+    AFTER masking (depth_metrics.h:66,154-161) while the trainers' computeDepthMetrics neither masks by range nor clamps
+    (tensorboard_trainer_enhanced.h:410-436) -- the two variants share accumulators in the kernel and must still come
+    out separately right (round-1 bug: rmse_log of the trainer variant counted clamped pixels twice)."""
+    B, H, W = 2, 64, 96
+    b = pkg.synth.make_batch(B, H, W, seed=61)
+    g = torch.Generator().manual_seed(7)
+    pred, gt = b["pred"].clone(), b["gt"].clone()
+    _plant(pred, [0.01, 0.05, 0.0999, 10.0001, 20.0, 55.0, 0.1, 10.0], 0.10, g)
+    _plant(gt, [0.05, 0.0999, 10.0001, 15.0, 30.0, 0.1, 10.0, 0.2], 0.05, g)
+    d = _dev()
+    for fused in (False, True):
+        if fused:
+            ws = pkg.stack_fwd_bwd(pred.to(d), gt.to(d), b["rgb"].to(d), b["K"].to(d), None, params=pkg.default_params(metrics=3))
+        else:
+            ws = pkg.metrics(pred.to(d), gt.to(d))
+        torch.cuda.synchronize()
+        r = pkg.results_dict(ws.read_results())
+        ev, evc = oracle.metrics_eval(pred.to(d), gt.to(d))
+        tr, trc = oracle.metrics_train(pred.to(d), gt.to(d))
+        assert r["eval_counts"] == evc and r["train_counts"] == trc, fused
+        assert trc[0] > evc[0]                     # the trainer variant keeps gt outside (0.1, 10)
+        for k in pkg.EVAL_KEYS:
+            assert rel_err(r["eval"][k], ev[k]) <= TOL, (fused, k, r["eval"][k], ev[k])
+        for k in pkg.TRAIN_KEYS:
+            assert rel_err(r["train"][k], tr[k]) <= TOL, (fused, k, r["train"][k], tr[k])
+
+
+@pytest.mark.parametrize("lo,hi,scale", [(0.0, 10.0, 1.0), (100.0, 10000.0, 1000.0), (1e-3, 80.0, 8.0)])
+def test_metrics_with_caller_chosen_depth_range(pkg, oracle, lo, hi, scale):
+    """DepthMetrics::compute(pred, gt, mask, min, max) forwards caller-chosen bounds (depth_metrics.h:40-46): min = 0,
+    millimetre depths with max > 1000 (above the clamp of the loss terms), a far range.  The metric logs are computed
+    from clamp(pred, min, max) and gt themselves, not borrowed from the scale-invariant term's clamp to [1e-6, 1000]."""
+    b = pkg.synth.make_batch(2, 48, 80, seed=62)
+    d = _dev()
+    pred, gt = (b["pred"] * scale).to(d), (b["gt"] * scale).to(d)
+    ws = pkg.metrics(pred, gt, which=pkg.METRICS_EVAL, min_depth=lo, max_depth=hi)
+    torch.cuda.synchronize()
+    r = pkg.results_dict(ws.read_results())
+    ev, evc = oracle.metrics_eval(pred, gt, None, lo, hi)
+    assert r["eval_counts"] == evc and evc[0] > 0
+    for k in pkg.EVAL_KEYS:
+        assert rel_err(r["eval"][k], ev[k]) <= TOL, (k, r["eval"][k], ev[k])
+
+
 def test_full_size_config3_properties(pkg, oracle):
     """BASELINE config 3 (32x480x640): vs the oracle on the same device, plus size-independent properties:
     linearity in upstream, determinism, count conservation, batch-permutation invariance of the loss."""

@@ -162,7 +162,7 @@ def test_batch_augment_matches_loader_restatement(pkg, oracle):
     """augmentSample (crop, flip, colour jitter) + the resize after it, per image, against the op-for-op restatement."""
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(11)
-    B, h, w, H, W = 6, 48, 64, 48, 64
+    B, h, w, H, W = 8, 48, 64, 48, 64
     rgb = torch.rand(B, 3, h, w, generator=g)
     depth = torch.rand(B, 1, h, w, generator=g) * 9 + 0.3
     K = torch.tensor([[55.0, 0, 31.5], [0, 56.0, 23.5], [0, 0, 1]]).repeat(B, 1, 1) * (1 + 0.01 * torch.arange(B).view(B, 1, 1))
@@ -174,6 +174,8 @@ def test_batch_augment_matches_loader_restatement(pkg, oracle):
         [0, 0, 0, 0, 0, 1, 1.13, 0.91],          # colour jitter
         [9, 7, 44, 33, 1, 1, 0.87, 1.08],        # all three
         [12, 9, 38, 28, 1, 0, 1.0, 1.0],
+        [1, 0, 64, 48, 1, 0, 1.0, 1.0],          # window overshoots by one column: clamped like the reference's Slice (:395-397)
+        [60, 44, 30, 30, 0, 0, 1.0, 1.0],        # overshoots in both directions
     ], dtype=torch.float32)
     ro, do, Ko = pkg.batch_augment(rgb.to(dev), depth.to(dev), K.to(dev), aug.to(dev), H, W)
     for b in range(B):

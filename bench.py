@@ -12,9 +12,12 @@ B=32 images of 480x640 per GPU (BASELINE config 3).  Prints ONE JSON line (rank 
   e2e       the same metric through the reference-facing C++ API (drop-in CombinedDepthLoss +
             DepthMetrics via host/libcadl_host.so) with pinned HOST buffers: H2D of pred/gt/rgb/K and the
             D2H of the loss scalar + metric blocks are inside the timed region
-  roofline  for the dominant kernel (phase_b_stream_kernel): algorithmic bytes (24 B/px: read pred, gt,
-            3 x rgb, write grad) / its CUDA-event duration (events recorded on the launching stream around each
-            launch of the step: cadl_debug_kernel_times), against MEASURED_PEAKS.json hbm_gbs
+  roofline  for the dominant kernel (stream3_kernel, the full-resolution gradient pass): algorithmic bytes (24 B/px:
+            read pred, gt, 3 x rgb, write grad) / its CUDA-event duration -- events recorded on the launching stream
+            around 20 back-to-back cadl_stack_grad calls after cadl_stack_prepare + cadl_stack_reduce have completed
+            (one launch each: the average launch duration) -- against MEASURED_PEAKS.json hbm_gbs
+  also      config 2 (reprojection alone), config 5's per-GPU shape (B=16 960x1280, reprojection + both metric
+            variants), and for N > 1 the exact-global-batch mode with both statistics exchanges
   cpu_baseline  the unmodified reference headers on LibTorch CPU (oracle/_ref) timed on this box
 
 --impl reference times the reference's own CPU implementation (same harness source compiled against the
@@ -250,23 +253,58 @@ def main():
     # ---- headline: K steps of the fused path, device-resident inputs (235 MB/step > 126 MB L2) ----
     with ClockSampler(local_rank) as clk:
         ms_step = timed(step, args.steps, args.warmup)
-        # per-phase durations for the roofline of the dominant kernel (same launches, timed apart)
-        params.pyramid_prepared = 0          # the phase timings below launch everything in line
-        ms_a = timed(lambda: pkg.stack_reduce(pred, gt, None, params, ws), args.steps, 3)
-        ms_b = timed(lambda: pkg.stack_grad(pred, gt, rgb, K, None, params, grad, ws), args.steps, 3)
-        # every launch of the step between its own pair of CUDA events (this mode synchronises after each step and
-        # switches the programmatic dependent launches off, so the intervals include the launch gaps)
-        per_launch = {}
-        pkg.kernel_times(True)
-        for _ in range(30):
-            step()
-            for name, ms in pkg.kernel_times(True):
-                per_launch.setdefault(name, []).append(ms)
-        pkg.kernel_times(False)
-        per_launch = {k: statistics.median(v) for k, v in per_launch.items()}
-        # config 2 (reprojection alone) as a secondary figure
+        # the dominant kernel alone: prepare (pyramid kernels) + reduce, wait for them, then ONE launch between two events
+        # on the launching stream (the product library has no per-kernel timing hook)
+        loc = pkg.default_params(metrics=pkg.METRICS_EVAL | pkg.METRICS_TRAIN)
+        ks, ka = [], []
+        NREP = 20
+        for it in range(2 + 10):
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            pkg.stack_prepare(pred, gt, loc, ws)
+            pkg.stack_reduce(pred, gt, None, loc, ws)
+            a1.record()
+            torch.cuda.synchronize()
+            # the statistics and the coarse-scale field stay valid: the gradient kernel can be launched again and again
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(NREP):
+                pkg.stack_grad(pred, gt, rgb, K, None, loc, grad, ws)
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                ks.append(e0.elapsed_time(e1) / NREP); ka.append(a0.elapsed_time(a1))
+        ms_k, ms_a = statistics.median(ks), statistics.median(ka)
+        also = []
+        # config 2 (reprojection alone)
         p2 = pkg.default_params(terms=pkg.TERM_REPROJ, w_reproj=1.0)
         ms_rp = timed(lambda: pkg.stack_fwd_bwd(pred, gt, None, K, None, params=p2, grad=grad, ws=ws), args.steps, 3)
+        # config 5, per-GPU shape: B=16 at 960x1280, reprojection + both metric variants
+        b5 = pkg.synth.make_batch(16, 960, 1280, seed=77 + rank, device=dev, with_rgb=False)
+        g5, ws5 = torch.empty_like(b5["pred"]), pkg.Workspace(16, 960, 1280, dev)
+        p5 = pkg.default_params(terms=pkg.TERM_REPROJ, w_reproj=1.0, metrics=pkg.METRICS_EVAL | pkg.METRICS_TRAIN)
+        ms_c5 = timed(lambda: pkg.stack_fwd_bwd(b5["pred"], b5["gt"], None, b5["K"], None, params=p5, grad=g5, ws=ws5),
+                      max(10, args.steps // 2), 3)
+        del b5, g5, ws5
+        # N > 1: the exact-global-batch mode, statistics exchanged by our peer-memory kernel and by NCCL
+        ms_global = {}
+        if world > 1:
+            gp = pkg.default_params(metrics=pkg.METRICS_EVAL | pkg.METRICS_TRAIN, global_B=B_PER_GPU * world)
+            ex = pkg.multi.P2PStatsExchange(pkg, dev)
+
+            def gstep(how):
+                pkg.stack_prepare(pred, gt, gp, ws)
+                pkg.stack_reduce(pred, gt, None, gp, ws)
+                if how == "p2p":
+                    ex.exchange(ws)
+                else:
+                    dist.all_reduce(ws.stats_view())
+                pkg.stack_grad(pred, gt, rgb, K, None, gp, grad, ws)
+            for how in ("p2p", "nccl"):
+                ms_global[how] = timed(lambda: gstep(how), args.steps, args.warmup)
+            ex.check()
+            ex.close()
         # the timed loops above last ~0.1 s in total: keep the same step running (untimed) for about a second so that
         # nvidia-smi (100 ms per query) sees the clocks UNDER this load, not an idle GPU
         t_end = time.perf_counter() + 1.2
@@ -278,24 +316,34 @@ def main():
     value = world * P / (ms_step * 1e-3) / 1e6
 
     peak, peak_src = hbm_peak()
-    ms_k = per_launch.get("phase_b_stream_kernel", ms_b)
     achieved = ALGO_BYTES_PER_PX * P / (ms_k * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "phase_b_stream_kernel<15,false>",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX * P,
-                "kernel_ms": ms_k, "phase_a_ms": ms_a, "phase_b_ms": ms_b,
-                "per_launch_ms": per_launch,
-                "step_frac": ALGO_BYTES_PER_PX * P / (ms_step * 1e-3) / 1e9 / peak}
+    traffic = None
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get("phase_b_stream_kernel_bytes_per_launch")
+            traffic = json.load(open(traffic_file)).get("stream3_kernel_bytes_per_launch")
         except Exception:
             pass
-    reproj = {"workload": "config2: reprojection alone fwd+bwd, B=32 480x640", "ms_per_step": ms_rp,
-              "value": world * P / (ms_rp * 1e-3) / 1e6, "unit": "Mpix/s",
-              "roofline_frac": ALGO_BYTES_PER_PX_REPROJ * P / (ms_rp * 1e-3) / 1e9 / peak}
+    roofline = {"bound": "hbm", "kernel": "stream3_kernel<15,false>",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic,
+                "traffic_source": "ncu --set full capture of the same kernel (profiles/traffic.json), static: not measured in this run",
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX * P,
+                "kernel_ms": ms_k, "first_stage_ms": ms_a,
+                "how": "CUDA events on the launching stream around 20 back-to-back cadl_stack_grad calls (one launch each), median of 10 such groups",
+                "step_frac": ALGO_BYTES_PER_PX * P / (ms_step * 1e-3) / 1e9 / peak}
+    also.append({"workload": "config2: reprojection alone fwd+bwd, B=32/GPU 480x640", "ms_per_step": ms_rp,
+                 "value": world * P / (ms_rp * 1e-3) / 1e6, "unit": "Mpix/s",
+                 "roofline_frac": ALGO_BYTES_PER_PX_REPROJ * P / (ms_rp * 1e-3) / 1e9 / peak})
+    P5 = 16 * 960 * 1280
+    also.append({"workload": "config5 shape: reprojection fwd+bwd + DepthMetrics + computeDepthMetrics, B=16/GPU 960x1280",
+                 "ms_per_step": ms_c5, "value": world * P5 / (ms_c5 * 1e-3) / 1e6, "unit": "Mpix/s", "n_gpus": world,
+                 "roofline_frac": ALGO_BYTES_PER_PX_REPROJ * P5 / (ms_c5 * 1e-3) / 1e9 / peak})
+    for how, ms in ms_global.items():
+        also.append({"workload": "config3, exact global-batch mode (statistics of all ranks before the gradient pass)",
+                     "stats_exchange": "peer-memory kernel over NVLink (cadl_stats_exchange)" if how == "p2p" else "NCCL all-reduce of 32 doubles",
+                     "ms_per_step": ms, "value": world * P / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "n_gpus": world})
 
     # ---- e2e: the drop-in C++ API with pinned host buffers (H2D + D2H inside the timed region) ----
     e2e = None
@@ -355,10 +403,9 @@ def main():
                        "l2": "inputs+gradient 275 MB per step > 126 MB L2 (no flush needed)",
                        "seed": "1234 + rank"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": 5 * args.steps,
-            "launches_per_step": ["phase_a_kernel<31,false>", "pyr_pool_kernel", "pyr_coef_kernel",
-                                  "phase_b_stream_kernel<15,false>", "stream_finish_kernel"],
-            "clocks": clocks, "also": reproj,
+            "gpu_launches": 4 * args.steps,
+            "launches_per_step": ["phase_a_kernel<31,false>", "pyr_pool_kernel", "pyr_coef_kernel", "stream3_kernel<15,false>"],
+            "clocks": clocks, "also": also,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

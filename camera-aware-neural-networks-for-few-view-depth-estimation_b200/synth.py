@@ -10,7 +10,7 @@ import math
 import torch
 
 
-def make_batch(B: int, H: int, W: int, seed: int = 1234, hole_frac: float = 0.15, device="cpu"):
+def make_batch(B: int, H: int, W: int, seed: int = 1234, hole_frac: float = 0.15, device="cpu", with_rgb: bool = True):
     """Returns dict(pred, gt, rgb, K, T): fp32, NCHW; gt has ~15 % zeros (invalid depth)."""
     g = torch.Generator().manual_seed(seed)
     gt = torch.empty(B, 1, H, W).uniform_(0.3, 9.8, generator=g)
@@ -20,7 +20,7 @@ def make_batch(B: int, H: int, W: int, seed: int = 1234, hole_frac: float = 0.15
     pred_h = torch.empty(B, 1, H, W).uniform_(0.05, 9.95, generator=g)
     pred = torch.where(holes, pred_h, pred)
     gt = torch.where(holes, torch.zeros_like(gt), gt)
-    rgb = torch.rand(B, 3, H, W, generator=g)
+    rgb = torch.rand(B, 3, H, W, generator=g) if with_rgb else torch.zeros(B, 3, 1, 1)      # (the big shapes that need no image)
     # Kinect-v1-like intrinsics rescaled to H x W (src/data/sunrgbd_loader.cpp:480-488), +-5 % jitter
     jit = 1.0 + 0.05 * (2.0 * torch.rand(B, 4, generator=g) - 1.0)
     K = torch.zeros(B, 3, 3)

@@ -34,6 +34,12 @@ class StepCfg:
     upstream: float = 1.0
 
 
+class _UNetCfg(C.Structure):
+    _fields_ = [("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("device", C.c_int), ("feats", C.c_int),
+                ("max_depth", C.c_float), ("lr", C.c_float), ("clip", C.c_float), ("fused_extras", C.c_int),
+                ("world", C.c_int), ("rank", C.c_int), ("bucket_mb", C.c_int)]
+
+
 def _f32(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
 
@@ -60,9 +66,72 @@ class StepHarness:
             L.cadh_clip_grad_norm.argtypes = [C.c_int, C.c_int, vp, vp, C.c_float, C.c_int, vp, vp, C.c_char_p, C.c_int]
             L.cadh_batch_prep.argtypes = [C.c_int] * 6 + [vp] * 6 + [C.c_char_p, C.c_int]
             L.cadh_accumulate.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_char_p, C.c_int]
+        L.cadh_metric_utils.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_char_p,
+                                        C.c_int, C.c_char_p, C.c_int]
+        if hasattr(L, "cadh_unet_train"):            # builds that saw the reference's model header
+            L.cadh_unet_train.argtypes = [C.POINTER(_UNetCfg), vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_char_p, C.c_int]
+        if hasattr(L, "cadh_nccl_init"):
+            L.cadh_nccl_unique_id.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+            L.cadh_nccl_init.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
         self.L = L
 
     # ------------------------------------------------------------------
+    def has_unet(self) -> bool:
+        return hasattr(self.L, "cadh_unet_train") and bool(self.L.cadh_has_unet())
+
+    def has_nccl(self) -> bool:
+        return hasattr(self.L, "cadh_nccl_init") and bool(self.L.cadh_has_nccl())
+
+    def nccl_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        err = C.create_string_buffer(2048)
+        if self.L.cadh_nccl_unique_id(buf, err, len(err)):
+            self._raise(err)
+        return buf.raw
+
+    def nccl_init(self, rank: int, world: int, unique_id: bytes, device: int):
+        err = C.create_string_buffer(2048)
+        if self.L.cadh_nccl_init(rank, world, unique_id, device, err, len(err)):
+            self._raise(err)
+
+    def nccl_finalize(self):
+        self.L.cadh_nccl_finalize()
+
+    def unet_train(self, rgb, gt, K, device: int = -1, feats: int = 64, max_depth: float = 10.0, lr: float = 1e-4,
+                   clip: float = 1.0, fused_extras: bool = False, world: int = 1, rank: int = 0, bucket_mb: int = 25,
+                   warmup: int = 1, iters: int = 3):
+        """BaselineUNet training-shaped steps (harness/unet_step.inc).  Returns dict(ms, loss_ms, last_loss, params,
+        grad_bytes, buckets)."""
+        rgb, gt, K = _f32(rgb), _f32(gt), _f32(K)
+        B, _, H, W = rgb.shape
+        cfg = _UNetCfg(B, H, W, device, feats, max_depth, lr, clip, int(fused_extras), world, rank, bucket_mb)
+        ms, lms = (C.c_double * iters)(), (C.c_double * iters)()
+        last = C.c_float(0)
+        info = (C.c_longlong * 3)()
+        err = C.create_string_buffer(2048)
+        rc = self.L.cadh_unet_train(C.byref(cfg), _p(rgb), _p(gt), _p(K), warmup, iters, ms, lms, C.byref(last), info, err, len(err))
+        if rc:
+            self._raise(err)
+        return {"ms": [float(x) for x in ms], "loss_ms": [float(x) for x in lms], "last_loss": float(last.value),
+                "params": int(info[0]), "grad_bytes": int(info[1]), "buckets": int(info[2])}
+
+    def metric_utils(self, device: int, pred, gt, mask=None, splits: int = 2):
+        """computePerSample / average / MetricsAccumulator / formatMetrics (depth_metrics.h:93-141, 259-333)."""
+        pred, gt = _f32(pred), _f32(gt)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        B, _, H, W = pred.shape
+        per = np.empty((B, 12), np.float32)
+        avg, acc = np.empty(12, np.float32), np.empty(12, np.float32)
+        cnt = (C.c_int * 2)()
+        text = C.create_string_buffer(4096)
+        err = C.create_string_buffer(2048)
+        rc = self.L.cadh_metric_utils(B, H, W, device, _p(pred), _p(gt), _p(m), splits, _p(per), _p(avg), _p(acc), cnt, text,
+                                      len(text), err, len(err))
+        if rc:
+            self._raise(err)
+        return {"per_sample": per, "average": avg, "accumulated": acc, "count": (int(cnt[0]), int(cnt[1])),
+                "text": text.value.decode()}
+
     def info(self) -> str:
         return self.L.cadh_build_info().decode()
 

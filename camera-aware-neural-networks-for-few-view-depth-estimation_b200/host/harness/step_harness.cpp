@@ -28,7 +28,9 @@
 
 #include "loss/depth_loss.h"
 #include "evaluation/depth_metrics.h"
-#ifdef CADL_DROPIN
+#ifndef CADL_DROPIN
+#include "ref_restatements.h"      // oracle/: what the reference keeps private or reports only as a float mean
+#else
 #include "training/validation_metrics.h"
 #include "training/grad_clip.h"
 #include "training/loss_accumulator.h"
@@ -107,74 +109,6 @@ int fail(char* err, int errlen, const std::exception& e) {
     return 1;
 }
 
-#ifndef CADL_DROPIN
-// Integer delta counts with the reference's own ops (depth_metrics.h:154-161,57-66,219-229):
-// the float mean the reference reports cannot hold counts above 2^24 exactly, so parity on
-// counts is defined against (ratio < thr).sum() of the same tensors.
-void ref_ops_eval_counts(torch::Tensor pred, torch::Tensor gt, torch::optional<torch::Tensor> user,
-                         float min_d, float max_d, int64_t counts[4]) {
-    if (pred.dim() == 3) pred = pred.unsqueeze(1);
-    if (gt.dim() == 3) gt = gt.unsqueeze(1);
-    auto mask = (gt > min_d) & (gt < max_d);
-    if (user.has_value()) {
-        auto um = user.value();
-        if (um.dim() == 3) um = um.unsqueeze(1);
-        mask = mask & um.to(torch::kBool);
-    }
-    auto p = pred.masked_select(mask);
-    auto g = gt.masked_select(mask);
-    counts[0] = p.numel();
-    counts[1] = counts[2] = counts[3] = 0;
-    if (counts[0] == 0) return;
-    p = torch::clamp(p, min_d, max_d);
-    auto ratio = torch::max(p / g, g / p);
-    float thr[3] = {1.25f, 1.25f * 1.25f, 1.25f * 1.25f * 1.25f};
-    for (int i = 0; i < 3; ++i) counts[1 + i] = (ratio < thr[i]).sum().item<int64_t>();
-}
-
-// Restatement, op for op, of the trainers' private computeDepthMetrics
-// (src/training/tensorboard_trainer_enhanced.h:400-439; duplicate at tensorboard_trainer.h:348-387).
-// The trainer headers cannot be included here: they pull in OpenCV.
-struct ValidationMetrics {
-    float loss = 0.0f, abs_rel = 0.0f, sq_rel = 0.0f, rmse = 0.0f, rmse_log = 0.0f;
-    float a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-};
-ValidationMetrics computeDepthMetrics(const torch::Tensor& pred, const torch::Tensor& gt) {
-    ValidationMetrics metrics;
-    auto pred_flat = pred.view({-1});
-    auto gt_flat = gt.view({-1});
-    auto valid_mask = gt_flat > 0.0f;
-    auto pred_valid = pred_flat.masked_select(valid_mask);
-    auto gt_valid = gt_flat.masked_select(valid_mask);
-    if (pred_valid.numel() == 0) return metrics;
-    auto abs_diff = torch::abs(pred_valid - gt_valid);
-    metrics.abs_rel = (abs_diff / gt_valid).mean().item<float>();
-    metrics.sq_rel = ((abs_diff * abs_diff) / gt_valid).mean().item<float>();
-    metrics.rmse = torch::sqrt((abs_diff * abs_diff).mean()).item<float>();
-    auto log_diff = torch::abs(torch::log(pred_valid + 1e-8) - torch::log(gt_valid + 1e-8));
-    metrics.rmse_log = torch::sqrt((log_diff * log_diff).mean()).item<float>();
-    auto ratio = torch::max(pred_valid / gt_valid, gt_valid / pred_valid);
-    metrics.a1 = (ratio < 1.25f).to(torch::kFloat32).mean().item<float>();
-    metrics.a2 = (ratio < 1.5625f).to(torch::kFloat32).mean().item<float>();
-    metrics.a3 = (ratio < 1.953125f).to(torch::kFloat32).mean().item<float>();
-    return metrics;
-}
-
-void ref_ops_train_counts(const torch::Tensor& pred, const torch::Tensor& gt, int64_t counts[4]) {
-    auto pf = pred.reshape({-1});
-    auto gf = gt.reshape({-1});
-    auto m = gf > 0.0f;
-    auto p = pf.masked_select(m);
-    auto g = gf.masked_select(m);
-    counts[0] = p.numel();
-    counts[1] = counts[2] = counts[3] = 0;
-    if (counts[0] == 0) return;
-    auto ratio = torch::max(p / g, g / p);
-    counts[1] = (ratio < 1.25f).sum().item<int64_t>();
-    counts[2] = (ratio < 1.5625f).sum().item<int64_t>();
-    counts[3] = (ratio < 1.953125f).sum().item<int64_t>();
-}
-#endif  // !CADL_DROPIN
 
 const char* kEvalKeys[12] = {"abs_rel", "sq_rel", "rmse", "rmse_log", "mae", "log10",
                              "delta_1.25", "delta_1.25^2", "delta_1.25^3",
@@ -366,6 +300,50 @@ int cadh_time_steps(const cadh_step_cfg* cfg, const float* pred, const float* gt
     }
 }
 
+// Host-side metric utilities (depth_metrics.h:93-141 computePerSample / average, :259-304 MetricsAccumulator,
+// :309-333 formatMetrics) driven the way an evaluation loop drives them: per-sample metrics of a batch, their average,
+// a running accumulator fed with `splits` consecutive sub-batches, and the printed block.
+//   out_per_sample: B x 12 floats (kEvalKeys order)     out_avg: 12     out_acc: 12 (accumulator average)
+//   out_count: accumulator count after the updates and after reset()     out_text: formatMetrics(average)
+int cadh_metric_utils(int B, int H, int W, int device, const float* pred, const float* gt, const uint8_t* mask,
+                      int splits, float* out_per_sample, float* out_avg, float* out_acc, int* out_count2, char* out_text,
+                      int textlen, char* err, int errlen) {
+    try {
+        cadh_step_cfg c{};
+        c.B = B; c.H = H; c.W = W; c.device = device;
+        auto dev = pick_device(device);
+        Batch b = to_device(c, pred, gt, nullptr, nullptr, mask, dev);
+        torch::NoGradGuard ng;
+        auto per = DepthMetrics::computePerSample(b.pred, b.gt, b.mask);
+        TORCH_CHECK((int)per.size() == B, "computePerSample returned ", per.size(), " maps for ", B, " samples");
+        for (int i = 0; i < B; ++i)
+            for (int k = 0; k < 12; ++k) out_per_sample[i * 12 + k] = per[i].at(kEvalKeys[k]);
+        auto avg = DepthMetrics::average(per);
+        for (int k = 0; k < 12; ++k) out_avg[k] = avg.at(kEvalKeys[k]);
+        MetricsAccumulator acc;
+        for (int sidx = 0; sidx < splits; ++sidx) {
+            const int lo = (int)((long long)B * sidx / splits), hi = (int)((long long)B * (sidx + 1) / splits);
+            if (hi <= lo) continue;
+            torch::optional<torch::Tensor> m;
+            if (b.mask.has_value()) m = b.mask.value().slice(0, lo, hi);
+            acc.update(DepthMetrics::compute(b.pred.slice(0, lo, hi), b.gt.slice(0, lo, hi), m));
+        }
+        auto am = acc.average();
+        for (int k = 0; k < 12; ++k) out_acc[k] = am.at(kEvalKeys[k]);
+        out_count2[0] = acc.count();
+        acc.reset();
+        out_count2[1] = acc.count();
+        const std::string text = formatMetrics(avg);
+        if (out_text && textlen > 0) {
+            std::strncpy(out_text, text.c_str(), textlen - 1);
+            out_text[textlen - 1] = 0;
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        return fail(err, errlen, e);
+    }
+}
+
 #ifdef CADL_DROPIN
 // "next" rows through their C++ wrappers (host/training/grad_clip.h, host/data/batch_prep.h)
 int cadh_clip_grad_norm(int device, int count, const float* const* grads_host, const int64_t* sizes, float max_norm,
@@ -427,3 +405,5 @@ int cadh_batch_prep(int device, int B, int h, int w, int H, int W, const float* 
 #endif
 
 }  // extern "C"
+
+#include "unet_step.inc"

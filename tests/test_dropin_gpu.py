@@ -148,3 +148,47 @@ def test_device_accumulator_cpp_wrapper(host):
     got = host.accumulate(0, vals, w)
     ref = float((vals.astype(np.float64) * w).sum() / w.sum())
     assert abs(got - ref) <= 1e-12 * abs(ref)
+
+
+def test_host_metric_utilities_match_the_reference_build(pkg, host, ref_harness):
+    """computePerSample, average, MetricsAccumulator::{update,average,count,reset} and formatMetrics (a10) through the
+    same harness source in both builds: the drop-in's C++ versions against the unmodified reference's."""
+    if ref_harness is None:
+        pytest.skip("oracle/_ref did not travel to this box")
+    b = pkg.synth.make_batch(5, 48, 64, seed=17)
+    z = {k: v.numpy() for k, v in b.items()}
+    g = torch.Generator().manual_seed(3)
+    mask = (torch.rand(5, 1, 48, 64, generator=g) < 0.7).numpy()
+    for m in (None, mask):
+        ours = host.metric_utils(0, z["pred"], z["gt"], m, splits=3)
+        ref = ref_harness.metric_utils(-1, z["pred"], z["gt"], m, splits=3)
+        assert ours["count"] == ref["count"] == (3, 0)
+        for key in ("per_sample", "average", "accumulated"):
+            a, r = np.asarray(ours[key], np.float64), np.asarray(ref[key], np.float64)
+            assert np.all(np.abs(a - r) <= TOL * np.maximum(np.abs(r), 1e-30)), (key, a, r)
+        # the printed block: same lines, numbers equal to the 4 printed decimals up to one unit of the last
+        la, lr = ours["text"].splitlines(), ref["text"].splitlines()
+        assert len(la) == len(lr) and len(la) >= 8
+        import re
+        for x, y in zip(la, lr):
+            assert re.sub(r"[-0-9.]+", "#", x) == re.sub(r"[-0-9.]+", "#", y), (x, y)
+            for u, v in zip(re.findall(r"-?[0-9]+\.[0-9]+", x), re.findall(r"-?[0-9]+\.[0-9]+", y)):
+                assert abs(float(u) - float(v)) <= 1.01e-4 * max(1.0, abs(float(v))), (x, y)
+
+
+def test_unet_training_step_with_the_dropin_loss(pkg, host, ref_harness):
+    """BASELINE config-4-shaped step, small: the reference's BaselineUNet (its header, included at build time) with the
+    drop-in CombinedDepthLoss on CUDA against the same step with the reference loss on CUDA: same seed, same data ->
+    the loss after a few Adam steps agrees (cuDNN convolutions are the common part; the loss path is what differs)."""
+    if not host.has_unet():
+        pytest.skip("host library was built without the reference's model header")
+    b = pkg.synth.make_batch(2, 64, 96, seed=5)
+    z = {k: v.numpy() for k, v in b.items()}
+    ours = host.unet_train(z["rgb"], z["gt"], z["K"], device=0, feats=16, warmup=0, iters=3)
+    assert ours["params"] > 0 and len(ours["ms"]) == 3 and all(t > 0 for t in ours["loss_ms"])
+    fused = host.unet_train(z["rgb"], z["gt"], z["K"], device=0, feats=16, fused_extras=True, warmup=0, iters=3)
+    assert abs(fused["last_loss"] - ours["last_loss"]) <= 0.6 * abs(ours["last_loss"])     # running mean vs last step
+    if ref_harness is not None and ref_harness.has_unet():
+        ref = ref_harness.unet_train(z["rgb"], z["gt"], z["K"], device=0, feats=16, warmup=0, iters=3)
+        assert ref["params"] == ours["params"]
+        assert abs(ref["last_loss"] - ours["last_loss"]) <= 2e-3 * abs(ref["last_loss"]), (ref["last_loss"], ours["last_loss"])

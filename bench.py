@@ -390,6 +390,25 @@ def main():
         cpu = {"value": P / (med * 1e-3) / 1e6, "unit": "Mpix/s", "cores": nthreads, "kind": kind,
                "sample": f"full config-3 batch (32x480x640), fwd+bwd + both metric variants, median of {len(ms)} "
                          f"steps after 1 warm-up, {med:.0f} ms/step"}
+        # the other CPU rows of BASELINE.md section 4 (reference build only): config 2 = reprojection alone on the same
+        # batch; config 1 = BaselineUNet(3,64,10) + full stack + clip + Adam, B=4 at 240x320
+        if kind == "reference":
+            others = []
+            ms2, _ = h.time_steps(pkg.StepCfg(device=-1, term=4), zc["pred"], zc["gt"], zc["rgb"], zc["K"],
+                                  with_metrics=False, include_h2d=False, warmup=1, iters=5)
+            m2 = statistics.median(ms2)
+            others.append({"workload": "config2: ReprojectionLoss::forward + backward, B=32 480x640, LibTorch CPU",
+                           "ms_per_step": m2, "value": P / (m2 * 1e-3) / 1e6, "unit": "Mpix/s"})
+            if h.has_unet():
+                b1 = pkg.synth.make_batch(4, 240, 320, seed=1234)
+                z1 = {k: v.numpy() for k, v in b1.items()}
+                r1 = h.unet_train(z1["rgb"], z1["gt"], z1["K"], device=-1, feats=64, warmup=1, iters=2)
+                m1, l1 = statistics.median(r1["ms"]), statistics.median(r1["loss_ms"])
+                others.append({"workload": "config1: BaselineUNet(3,64,10) training step (forward, forwardWithIntrinsics, "
+                                           "backward, clip_grad_norm_, Adam), B=4 240x320, LibTorch CPU",
+                               "ms_per_step": m1, "samples_per_s": 4 / (m1 * 1e-3), "loss_forward_ms": l1,
+                               "value": 4 * 240 * 320 / (m1 * 1e-3) / 1e6, "unit": "Mpix/s", "params": r1["params"]})
+            cpu["others"] = others
 
     if rank == 0:
         line = {

@@ -372,7 +372,11 @@ cudaError_t launch_point_fast(PhaseBArgs& a, cudaStream_t st) {
     // (the earlier sizing assumed 8 per SM and ran 1.6 waves); its warps deal the image's 128-pixel row segments
     // round-robin.  b_rows = grid size (partial rows, ticket).
     const int wpb = kThreadsB / 32;
-    int bpi = (4 * num_sms_cached()) / a.B;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, a.mask ? (const void*)phase_b_point_fast_kernel<F, true>
+                                                                       : (const void*)phase_b_point_fast_kernel<F, false>,
+                                                      kThreadsB, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    int bpi = (per_sm * num_sms_cached()) / a.B;
     const int max_bpi = (a.H * ((a.W + 127) / 128) + wpb - 1) / wpb;        // at least one segment per warp
     if (bpi > max_bpi) bpi = max_bpi;
     while (bpi > 1 && bpi * a.B > kPointBlocks) --bpi;
@@ -391,14 +395,14 @@ cudaError_t launch_point_count(PhaseBArgs& a, cudaStream_t st) {
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, current_device() < 0 ? 0 : current_device());
     if (!coop) return cudaErrorNotSupported;
     const int wpb = kThreadsB / 32;
-    int bpi = (4 * num_sms_cached()) / a.B;
-    const int max_bpi = (a.H * ((a.W + 127) / 128) + wpb - 1) / wpb;
-    if (bpi > max_bpi) bpi = max_bpi;
-    if (bpi < 1) return cudaErrorNotSupported;                    // more images than resident CTAs
     void* fn = a.mask ? (void*)phase_b_point_fast_kernel<FB_RP, true, true> : (void*)phase_b_point_fast_kernel<FB_RP, false, true>;
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreadsB, 0);
     if (e != cudaSuccess) return e;
+    int bpi = (per_sm * num_sms_cached()) / a.B;
+    const int max_bpi = (a.H * ((a.W + 127) / 128) + wpb - 1) / wpb;
+    if (bpi > max_bpi) bpi = max_bpi;
+    if (bpi < 1) return cudaErrorNotSupported;                    // more images than resident CTAs
     if ((long long)bpi * a.B > (long long)per_sm * num_sms_cached()) return cudaErrorNotSupported;
     dim3 grid(bpi, a.B);
     a.b_rows = bpi * a.B;

@@ -699,8 +699,14 @@ __global__ void __launch_bounds__(kThreadsB, 2) phase_b_fast_kernel(const PhaseB
 // COUNT (reprojection alone, cooperative launch): the kernel counts the valid pixels itself in a first sweep over gt
 // (the only statistic this term needs), meets at a grid-wide barrier, and then runs the gradient sweep -- no separate
 // phase-A launch, no reduce-kernel epilogue, no launch gap (~8 us of a 43 us step at config 2).
+#ifndef CADL_PT_MINB
+#define CADL_PT_MINB 3
+#endif
+#ifndef CADL_PT_NB
+#define CADL_PT_NB 3
+#endif
 template <int F, bool HAS_MASK, bool COUNT = false>
-__global__ void __launch_bounds__(kThreadsB, 4) phase_b_point_fast_kernel(const PhaseBArgs a) {
+__global__ void __launch_bounds__(kThreadsB, CADL_PT_MINB) phase_b_point_fast_kernel(const PhaseBArgs a) {
     __shared__ float s_f[kThreadsB / 32][BF_COUNT];
     __shared__ double s_d[8];
     __shared__ float s_c[4];
@@ -787,9 +793,11 @@ __global__ void __launch_bounds__(kThreadsB, 4) phase_b_point_fast_kernel(const 
     // Work items = 128-pixel row segments of this image, dealt round-robin to the warps of the image's CTAs (whole
     // rows per warp left some warps with 4 rows and others with 3 at config 2).  NB items per batch: all loads of
     // a batch are issued before any arithmetic.
+    const float2 rfx2 = make_float2(rfx, rfx), rfy2 = make_float2(rfy, rfy), fxe2 = make_float2(fxe, fxe), fye2 = make_float2(fye, fye);
+    float2 acc2 = make_float2(0.f, 0.f);     // sum of e, two lanes of the packed pipe
     const int wstride = gridDim.x * (kThreadsB / 32);
     const int items = H * segs;
-    constexpr int NB = 3;
+    constexpr int NB = CADL_PT_NB;
     // (row, segment) of an item advance by a fixed (dq, dr) per stride: no integer division in the loop
     const int dq = wstride / segs, dr = wstride - dq * segs;
     int i0 = blockIdx.x * (kThreadsB / 32) + warp;
@@ -843,35 +851,47 @@ __global__ void __launch_bounds__(kThreadsB, 4) phase_b_point_fast_kernel(const 
               const bool m = HAS_MASK ? um[k] : (g[k] > eps_s);
               if (m && in_range_pos(p[k], eps_s, 1000.0f)) gsum = fmaf(c1, lp[k] - lg[k], c2) * rcp_approx(p[k]);
             }
-            if constexpr (RP) {
-              const bool m = HAS_MASK ? um[k] : (g[k] > eps_r);
-              if (m) {
-                const float ax = (xf + (float)k) - cxv;            // (float)(x+k) is exact; depth_loss.h:299
-                float pX, gX, pY, gY;
-                if (mk_ok) {
-                  pX = div_by_const(__fmul_rn(ax, p[k]), fxe, rfx);
-                  gX = div_by_const(__fmul_rn(ax, g[k]), fxe, rfx);
-                  pY = div_by_const(__fmul_rn(ayv, p[k]), fye, rfy);
-                  gY = div_by_const(__fmul_rn(ayv, g[k]), fye, rfy);
-                } else {
-                  pX = __fdiv_rn(__fmul_rn(ax, p[k]), fxe);
-                  gX = __fdiv_rn(__fmul_rn(ax, g[k]), fxe);
-                  pY = __fdiv_rn(__fmul_rn(ayv, p[k]), fye);
-                  gY = __fdiv_rn(__fmul_rn(ayv, g[k]), fye);
-                }
-                const float dX = pX - gX, dY = pY - gY, dZ = p[k] - g[k];
-                const float ss = fmaf(dZ, dZ, fmaf(dY, dY, dX * dX)) + eps_r;   // :313-315
-                const float re = rsqrt_approx(ss);
-                acc[BF_RP_E] = fmaf(ss, re, acc[BF_RP_E]);
-                gsum = fmaf(fmaf(dX, ax * rfx, fmaf(dY, yh, dZ)) * re, rpn, gsum);
-              }
-            }
             out[k] = gsum;
+          }
+          if constexpr (RP) {
+            // same operations, same order as depth_loss.h:299-315 -- X = ((u - cx) * d) / (fx + eps) -- two pixels
+            // per instruction on the packed fp32x2 pipes (the pairs line up with the float4 loads)
+            const float2 ay2 = make_float2(ayv, ayv), yh2 = make_float2(yh, yh);
+            const float2 rpn2 = make_float2(rpn, rpn), eps2 = make_float2(eps_r, eps_r);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float2 pp = make_float2(p[2 * h], p[2 * h + 1]), gg = make_float2(g[2 * h], g[2 * h + 1]);
+              const float2 ax = make_float2((xf + (float)(2 * h)) - cxv, (xf + (float)(2 * h + 1)) - cxv);   // (float)(x+k) is exact
+              const float2 xh = __fmul2_rn(ax, rfx2);
+              const float2 tpx = __fmul2_rn(ax, pp), tgx = __fmul2_rn(ax, gg), tpy = __fmul2_rn(ay2, pp), tgy = __fmul2_rn(ay2, gg);
+              float2 pX, gX, pY, gY;
+              if (mk_ok) {
+                // Markstein: q0 = t * rb, rem = t - q0 * b (exact), q = q0 + rem * rb = RN(t / b)
+                float2 q0 = __fmul2_rn(tpx, rfx2); pX = __ffma2_rn(__ffma2_rn(make_float2(-q0.x, -q0.y), fxe2, tpx), rfx2, q0);
+                q0 = __fmul2_rn(tgx, rfx2);        gX = __ffma2_rn(__ffma2_rn(make_float2(-q0.x, -q0.y), fxe2, tgx), rfx2, q0);
+                q0 = __fmul2_rn(tpy, rfy2);        pY = __ffma2_rn(__ffma2_rn(make_float2(-q0.x, -q0.y), fye2, tpy), rfy2, q0);
+                q0 = __fmul2_rn(tgy, rfy2);        gY = __ffma2_rn(__ffma2_rn(make_float2(-q0.x, -q0.y), fye2, tgy), rfy2, q0);
+              } else {
+                pX = make_float2(__fdiv_rn(tpx.x, fxe), __fdiv_rn(tpx.y, fxe)); gX = make_float2(__fdiv_rn(tgx.x, fxe), __fdiv_rn(tgx.y, fxe));
+                pY = make_float2(__fdiv_rn(tpy.x, fye), __fdiv_rn(tpy.y, fye)); gY = make_float2(__fdiv_rn(tgy.x, fye), __fdiv_rn(tgy.y, fye));
+              }
+              const float2 dX = __fadd2_rn(pX, make_float2(-gX.x, -gX.y)), dY = __fadd2_rn(pY, make_float2(-gY.x, -gY.y));
+              const float2 dZ = __fadd2_rn(pp, make_float2(-gg.x, -gg.y));
+              const float2 ss = __fadd2_rn(__ffma2_rn(dZ, dZ, __ffma2_rn(dY, dY, __fmul2_rn(dX, dX))), eps2);   // :313-315
+              float2 re = make_float2(rsqrt_approx(ss.x), rsqrt_approx(ss.y));
+              const bool m0 = HAS_MASK ? um[2 * h] : (gg.x > eps_r), m1 = HAS_MASK ? um[2 * h + 1] : (gg.y > eps_r);
+              re.x = m0 ? re.x : 0.f; re.y = m1 ? re.y : 0.f;
+              acc2 = __ffma2_rn(ss, re, acc2);                                                    // e = sqrt(ss)
+              const float2 t = __fmul2_rn(__ffma2_rn(dX, xh, __ffma2_rn(dY, yh2, dZ)), re);
+              const float2 o = __ffma2_rn(t, rpn2, make_float2(out[2 * h], out[2 * h + 1]));
+              out[2 * h] = o.x; out[2 * h + 1] = o.y;
+            }
           }
           if (a.grad) *reinterpret_cast<float4*>(a.grad + off) = make_float4(out[0], out[1], out[2], out[3]);
         }
       }
     }
+    acc[BF_RP_E] = acc2.x + acc2.y;
     if (publish_partials(a, acc, blockIdx.y * gridDim.x + blockIdx.x, s_f, &s_last)) {
         if (COUNT && tid == 0) a.hdr->icount[AI_RP_N] = 0ull;      // everybody has read it: leave the counter clean
         finalize_results(a, s_d);

@@ -1020,6 +1020,8 @@ int cadl_photometric_fwd_bwd(const float* pred, const float* K, int k_batched, c
     if (!pred || !K || !T || !source || !target || !results) return CADL_ERR_NULL;
     int rc = check_common(B, H, W, workspace, workspace_bytes);
     if (rc) return rc;
+    if (W % 4 != 0 || !aligned(pred, 16) || !aligned(target, 16) || (grad_pred && !aligned(grad_pred, 16)))
+        return CADL_ERR_UNSUPPORTED;              // 128-bit rows (every BASELINE shape)
     Ws ws = make_ws(workspace, B, H, W);
     return cuda_rc(launch_photometric(pred, K, k_batched, T, source, target, B, H, W, eps, upstream, grad_pred,
                                       results, ws.hdr(), ws.b_part(), kPointBlocks, ws.img_off(),

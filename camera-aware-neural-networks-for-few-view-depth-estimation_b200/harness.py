@@ -66,6 +66,7 @@ class StepHarness:
             L.cadh_clip_grad_norm.argtypes = [C.c_int, C.c_int, vp, vp, C.c_float, C.c_int, vp, vp, C.c_char_p, C.c_int]
             L.cadh_batch_prep.argtypes = [C.c_int] * 6 + [vp] * 6 + [C.c_char_p, C.c_int]
             L.cadh_accumulate.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_char_p, C.c_int]
+            L.cadh_photometric_step.argtypes = [C.c_int] * 4 + [vp] * 5 + [C.c_float, vp, vp, C.c_char_p, C.c_int]
         L.cadh_metric_utils.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_char_p,
                                         C.c_int, C.c_char_p, C.c_int]
         if hasattr(L, "cadh_unet_train"):            # builds that saw the reference's model header
@@ -232,6 +233,19 @@ class StepHarness:
         if rc:
             self._raise(err)
         return float(out.value)
+
+    def photometric_step(self, device: int, pred, K, T, src, tgt, upstream: float = 1.0):
+        """ReprojectionLoss::forwardPhotometricWarp + backward (host/loss/depth_loss.h) -> (loss, dL/dpred)."""
+        pred, K, T, src, tgt = _f32(pred), _f32(K), _f32(T), _f32(src), _f32(tgt)
+        B, _, H, W = pred.shape
+        loss = C.c_float(0)
+        grad = np.empty_like(pred)
+        err = C.create_string_buffer(2048)
+        rc = self.L.cadh_photometric_step(B, H, W, device, _p(pred), _p(K), _p(T), _p(src), _p(tgt), upstream,
+                                          C.byref(loss), _p(grad), err, len(err))
+        if rc:
+            self._raise(err)
+        return float(loss.value), grad
 
     def batch_prep(self, device: int, rgb, depth, K, H: int, W: int):
         """resizeBatchOnDevice (host/data/batch_prep.h)."""

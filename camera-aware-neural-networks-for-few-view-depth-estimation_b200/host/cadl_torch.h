@@ -176,6 +176,46 @@ struct FusedLossFunction : public torch::autograd::Function<FusedLossFunction> {
     }
 };
 
+// Autograd node of the opt-in photometric warp (ReprojectionLoss::forwardPhotometricWarp): same shape as
+// FusedLossFunction -- forward() runs forward + backward kernels, backward() scales the stored gradient.
+struct PhotometricFunction : public torch::autograd::Function<PhotometricFunction> {
+    static torch::Tensor forward(torch::autograd::AutogradContext* ctx, torch::Tensor pred, torch::Tensor K, torch::Tensor T,
+                                 torch::Tensor src, torch::Tensor tgt, int64_t batched, double eps, bool want_grad) {
+        const auto dev = pred.device();
+        c10::cuda::CUDAGuard guard(dev);
+        const int B = (int)pred.size(0), H = (int)pred.size(2), W = (int)pred.size(3);
+        size_t ws_bytes = 0;
+        auto ws = workspace_for(dev, B, H, W, &ws_bytes);
+        auto results = new_results(dev);
+        torch::Tensor grad;
+        if (want_grad) grad = torch::empty_like(pred);
+        int rc = cadl_photometric_fwd_bwd(pred.data_ptr<float>(), K.data_ptr<float>(), (int)batched, T.data_ptr<float>(),
+                                          src.data_ptr<float>(), tgt.data_ptr<float>(), B, H, W, (float)eps, 1.0f,
+                                          grad.defined() ? grad.data_ptr<float>() : nullptr,
+                                          reinterpret_cast<cadl_results*>(results.data_ptr<uint8_t>()), ws.data_ptr<uint8_t>(),
+                                          ws_bytes, current_stream(dev));
+        check_rc(rc, "cadl_photometric_fwd_bwd");
+        if (want_grad) ctx->save_for_backward({grad});
+        return result_scalar(results, offsetof(cadl_results, loss_reproj));
+    }
+    static torch::autograd::variable_list backward(torch::autograd::AutogradContext* ctx,
+                                                   torch::autograd::variable_list grad_outputs) {
+        auto saved = ctx->get_saved_variables();
+        TORCH_CHECK(saved.size() == 1, "cadl: backward without a stored gradient");
+        auto go = grad_outputs[0];
+        TORCH_CHECK(go.defined() && go.numel() == 1, "cadl: the loss is a scalar");
+        const auto dev = saved[0].device();
+        c10::cuda::CUDAGuard guard(dev);
+        go = go.to(dev, torch::kFloat32).contiguous();
+        auto out = saved[0].clone();              // (a copy: the node may be run again with retain_graph)
+        int rc = cadl_scale_grad(out.data_ptr<float>(), go.data_ptr<float>(), out.data_ptr<float>(), (size_t)out.numel(),
+                                 current_stream(dev));
+        check_rc(rc, "cadl_scale_grad");
+        torch::Tensor none;
+        return {out, none, none, none, none, none, none, none};
+    }
+};
+
 struct TermCall {
     cadl_params p;
     size_t result_offset;

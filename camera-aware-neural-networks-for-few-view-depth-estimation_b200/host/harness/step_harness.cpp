@@ -345,6 +345,29 @@ int cadh_metric_utils(int B, int H, int W, int device, const float* pred, const 
 }
 
 #ifdef CADL_DROPIN
+// ReprojectionLoss::forwardPhotometricWarp (opt-in extension) + backward: loss and dL/dpred
+int cadh_photometric_step(int B, int H, int W, int device, const float* pred, const float* K, const float* T,
+                          const float* src, const float* tgt, float upstream, float* out_loss, float* out_grad, char* err,
+                          int errlen) {
+    try {
+        auto dev = pick_device(device);
+        auto p = host_view(pred, {B, 1, H, W}).to(dev).clone().set_requires_grad(true);
+        auto k = host_view(K, {B, 3, 3}).to(dev);
+        auto t = host_view(T, {B, 4, 4}).to(dev);
+        auto s_ = host_view(src, {B, 3, H, W}).to(dev);
+        auto g_ = host_view(tgt, {B, 3, H, W}).to(dev);
+        ReprojectionLoss l;
+        auto loss = l.forwardPhotometricWarp(p, k, t, s_, g_);
+        (loss * upstream).backward();
+        *out_loss = loss.item<float>();
+        auto gh = p.grad().to(torch::kCPU).contiguous();
+        std::memcpy(out_grad, gh.data_ptr<float>(), sizeof(float) * gh.numel());
+        return 0;
+    } catch (const std::exception& e) {
+        return fail(err, errlen, e);
+    }
+}
+
 // "next" rows through their C++ wrappers (host/training/grad_clip.h, host/data/batch_prep.h)
 int cadh_clip_grad_norm(int device, int count, const float* const* grads_host, const int64_t* sizes, float max_norm,
                         int do_clip, float* out2, float* const* grads_out_host, char* err, int errlen) {

@@ -134,6 +134,29 @@ public:
         return torch::zeros(1, pred_depth.options());
     }
 
+    /// OPT-IN EXTENSION (not in the reference, whose forwardPhotometric is the stub above): the photometric
+    /// reprojection documents/algorithms_and_theory.md:18-77 describes -- back-project target pixels with pred depth
+    /// and K, move them with T = [R|t] (B,4,4 row-major, target -> source), project with K, sample source_image
+    /// bilinearly (grid_sample convention of src/layers/pcl_layer.h:104-108: zeros padding, align_corners = false)
+    /// and average the channel-mean L1 residual over the pixels that land inside the source image with Z > eps.
+    /// Differentiable w.r.t. pred_depth (explicit backward kernel).  Returns a 0-dim tensor; zeros when no pixel is valid.
+    torch::Tensor forwardPhotometricWarp(torch::Tensor pred_depth, torch::Tensor intrinsics, torch::Tensor pose,
+                                         torch::Tensor source_image, torch::Tensor target_image) {
+        using namespace cadl_detail;
+        auto pred = as_input(pred_depth, "pred_depth", 1);
+        auto src = as_input(source_image, "source_image", 3);
+        auto tgt = as_input(target_image, "target_image", 3);
+        TORCH_CHECK(src.sizes() == tgt.sizes() && src.size(0) == pred.size(0) && src.size(2) == pred.size(2) &&
+                    src.size(3) == pred.size(3), "cadl: images and depth differ in shape");
+        int batched = 1;
+        auto K = as_intrinsics(intrinsics, pred.size(0), pred.device(), batched);
+        TORCH_CHECK(pose.defined() && pose.scalar_type() == torch::kFloat32 && pose.device() == pred.device() &&
+                    pose.dim() == 3 && pose.size(0) == pred.size(0) && pose.size(1) == 4 && pose.size(2) == 4,
+                    "cadl: pose must be a float32 (B,4,4) tensor on pred's device");
+        const bool want_grad = pred.requires_grad() && torch::GradMode::is_enabled();
+        return PhotometricFunction::apply(pred, K, pose.contiguous(), src, tgt, (int64_t)batched, (double)eps_, want_grad);
+    }
+
     float eps() const { return eps_; }
 
 private:

@@ -66,6 +66,7 @@ class StepHarness:
             L.cadh_clip_grad_norm.argtypes = [C.c_int, C.c_int, vp, vp, C.c_float, C.c_int, vp, vp, C.c_char_p, C.c_int]
             L.cadh_batch_prep.argtypes = [C.c_int] * 6 + [vp] * 6 + [C.c_char_p, C.c_int]
             L.cadh_accumulate.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_char_p, C.c_int]
+            L.cadh_rays_roundtrip.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.c_char_p, C.c_int, vp, vp, vp, C.c_char_p, C.c_int]
             L.cadh_photometric_step.argtypes = [C.c_int] * 4 + [vp] * 5 + [C.c_float, vp, vp, C.c_char_p, C.c_int]
         L.cadh_metric_utils.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_char_p,
                                         C.c_int, C.c_char_p, C.c_int]
@@ -233,6 +234,20 @@ class StepHarness:
         if rc:
             self._raise(err)
         return float(out.value)
+
+    def rays_roundtrip(self, device: int, K33, H: int, W: int, path: str, corrupt_dims: bool = False):
+        """RayDirectionComputer::computeRayDirections -> saveRayDirections -> loadRayDirections (host/preprocessing).
+        Returns (saved?, rays (H*W,3) or None, (h, w))."""
+        K33 = _f32(K33)
+        out = np.empty((H * W, 3), np.float32)
+        saved = C.c_int(0)
+        hw = (C.c_int * 2)()
+        err = C.create_string_buffer(2048)
+        rc = self.L.cadh_rays_roundtrip(device, H, W, _p(K33), path.encode(), int(corrupt_dims), _p(out), C.byref(saved), hw,
+                                        err, len(err))
+        if rc:
+            self._raise(err)
+        return bool(saved.value), (out if saved.value else None), (int(hw[0]), int(hw[1]))
 
     def photometric_step(self, device: int, pred, K, T, src, tgt, upstream: float = 1.0):
         """ReprojectionLoss::forwardPhotometricWarp + backward (host/loss/depth_loss.h) -> (loss, dL/dpred)."""

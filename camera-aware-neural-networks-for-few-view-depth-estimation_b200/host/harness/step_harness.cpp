@@ -35,6 +35,7 @@
 #include "training/grad_clip.h"
 #include "training/loss_accumulator.h"
 #include "data/batch_prep.h"
+#include "preprocessing/ray_directions.h"
 #endif
 
 using namespace camera_aware_depth;
@@ -362,6 +363,26 @@ int cadh_photometric_step(int B, int H, int W, int device, const float* pred, co
         *out_loss = loss.item<float>();
         auto gh = p.grad().to(torch::kCPU).contiguous();
         std::memcpy(out_grad, gh.data_ptr<float>(), sizeof(float) * gh.numel());
+        return 0;
+    } catch (const std::exception& e) {
+        return fail(err, errlen, e);
+    }
+}
+
+// RayDirectionComputer drop-in: rays of ONE camera on the device -> saveRayDirections -> loadRayDirections.
+// out_rays: H*W*3 floats as loaded back; returns the save() result in *saved (0: the reference's "false" paths).
+int cadh_rays_roundtrip(int device, int H, int W, const float* K9, const char* path, int corrupt_dims, float* out_rays,
+                        int* saved, int* hw_out, char* err, int errlen) {
+    try {
+        auto dev = pick_device(device);
+        auto K = host_view(K9, {3, 3}).to(dev);
+        auto rays = RayDirectionComputer::computeRayDirections(K, H, W)[0];
+        *saved = RayDirectionComputer::saveRayDirections(rays, corrupt_dims ? H + 1 : H, W, path) ? 1 : 0;
+        if (!*saved) return 0;
+        int h = 0, w = 0;
+        auto back = RayDirectionComputer::loadRayDirections(path, h, w);
+        hw_out[0] = h; hw_out[1] = w;
+        std::memcpy(out_rays, back.data_ptr<float>(), sizeof(float) * (size_t)back.numel());
         return 0;
     } catch (const std::exception& e) {
         return fail(err, errlen, e);

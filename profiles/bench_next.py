@@ -96,6 +96,28 @@ def main():
                       "speedup_vs_torch": ref / ours, "speedup_vs_reference_loop": (loop + ref) / ours,
                       "workload": f"{len(sizes)} tensors, {n_el} elements"}))
 
+    # ---- rays: unit ray maps for a batch of cameras (store-bound: 12 B/px written) ----
+    Bk = 32
+    Kb = pkg.synth.make_batch(Bk, 480, 640, seed=3, with_rgb=False)["K"].to(dev)
+    for layout, name in ((1, "planar (B,3,H,W): the loader's layout"), (0, "(B,H*W,3): computeRayDirections' layout")):
+        ms = timeit(lambda: pkg.rays_from_K(Kb, 480, 640, layout=layout), flush=flush)
+        by = 12 * Bk * 480 * 640
+        print(json.dumps({"row": "rays_from_K", "layout": name, "ms": ms, "GBps": by / ms / 1e6, "frac_of_hbm": by / ms / 1e6 / hbm,
+                          "workload": f"B={Bk} 480x640, 12 B/px written"}))
+
+    # ---- photometric warp (opt-in extension): 32 B/px (depth 4, target 12, source 12 through L2, gradient 4) ----
+    Bp, Hp, Wp = 32, 480, 640
+    bp = pkg.synth.make_batch(Bp, Hp, Wp, seed=5, device=dev)
+    src = torch.rand(Bp, 3, Hp, Wp, device=dev, generator=g)
+    depth = (2.0 + bp["pred"] * 0.3).contiguous()
+    T = bp["T"].clone()
+    T[:, 0, 3] = 0.05
+    wsp = pkg.Workspace(Bp, Hp, Wp, dev)
+    ms = timeit(lambda: pkg.photometric_fwd_bwd(depth, bp["K"], T, src, bp["rgb"], ws=wsp), flush=flush)
+    by = 32 * Bp * Hp * Wp
+    print(json.dumps({"row": "photometric_fwd_bwd", "ms": ms, "GBps": by / ms / 1e6, "frac_of_hbm": by / ms / 1e6 / hbm,
+                      "Mpix_per_s": Bp * Hp * Wp / ms / 1e3, "workload": f"B={Bp} {Hp}x{Wp}, <=10 degree tilt + 5 cm baseline, 32 B/px"}))
+
 
 if __name__ == "__main__":
     main()

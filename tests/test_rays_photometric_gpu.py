@@ -70,6 +70,36 @@ def test_rays_bin_roundtrip_from_device(pkg, tmp_path):
     assert np.array_equal(back.reshape(H, W, 3).transpose(2, 0, 1), planar)
 
 
+def test_rays_cpp_codec_matches_the_python_codec_and_the_reference_format(pkg, tmp_path):
+    """host/preprocessing/ray_directions.h (the drop-in RayDirectionComputer): device rays -> saveRayDirections ->
+    loadRayDirections in C++; the file is byte-identical to the Python codec's and to the format of
+    ray_direction_computer.h:96-99 (int32 H, int32 W, H*W*3 float32); a dimension mismatch returns false (.cpp:146-152)."""
+    H, W = 48, 64
+    b = pkg.synth.make_batch(1, H, W, seed=3)
+    host = pkg.host_harness()
+    f_cpp, f_py = str(tmp_path / "cpp.bin"), str(tmp_path / "py.bin")
+    ok, back, hw = host.rays_roundtrip(0, b["K"][0].numpy(), H, W, f_cpp)
+    assert ok and hw == (H, W)
+    dev_rays = pkg.rays_from_K(b["K"].cuda(), H, W, layout=0).cpu().numpy()[0]
+    assert np.array_equal(back, dev_rays)
+    assert pkg.save_ray_directions(dev_rays, H, W, f_py)
+    assert open(f_cpp, "rb").read() == open(f_py, "rb").read()
+    raw = open(f_cpp, "rb").read()
+    assert len(raw) == 8 + H * W * 12 and np.frombuffer(raw[:8], "<i4").tolist() == [H, W]
+    ok, _, _ = host.rays_roundtrip(0, b["K"][0].numpy(), H, W, str(tmp_path / "bad.bin"), corrupt_dims=True)
+    assert not ok
+
+
+@pytest.mark.parametrize("W", [64, 52, 50])       # 128-bit path, 4-aligned odd count of quads, scalar path
+def test_rays_layouts_agree_for_any_width(pkg, W):
+    H = 24
+    b = pkg.synth.make_batch(2, H, W, seed=9)
+    r0 = pkg.rays_from_K(b["K"].cuda(), H, W, layout=0).cpu()
+    r1 = pkg.rays_from_K(b["K"].cuda(), H, W, layout=1).cpu()
+    assert torch.equal(r0.view(2, H, W, 3).permute(0, 3, 1, 2), r1)
+    assert float((r0.norm(dim=-1) - 1).abs().max()) < 1e-6
+
+
 def _smooth_images(B, H, W, seed):
     g = torch.Generator().manual_seed(seed)
     yy = torch.linspace(0, 1, H).view(1, 1, H, 1)

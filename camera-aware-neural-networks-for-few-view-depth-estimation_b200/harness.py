@@ -66,6 +66,7 @@ class StepHarness:
             L.cadh_clip_grad_norm.argtypes = [C.c_int, C.c_int, vp, vp, C.c_float, C.c_int, vp, vp, C.c_char_p, C.c_int]
             L.cadh_batch_prep.argtypes = [C.c_int] * 6 + [vp] * 6 + [C.c_char_p, C.c_int]
             L.cadh_accumulate.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_char_p, C.c_int]
+            L.cadh_empty_rank.argtypes = [C.c_int] * 4 + [vp] * 4 + [C.c_char_p, C.c_int]
             L.cadh_rays_roundtrip.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.c_char_p, C.c_int, vp, vp, vp, C.c_char_p, C.c_int]
             L.cadh_photometric_step.argtypes = [C.c_int] * 4 + [vp] * 5 + [C.c_float, vp, vp, C.c_char_p, C.c_int]
         L.cadh_metric_utils.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_char_p,
@@ -234,6 +235,16 @@ class StepHarness:
         if rc:
             self._raise(err)
         return float(out.value)
+
+    def empty_rank(self, device: int, pred, gt, K):
+        """dim() of ScaleInvariantLoss / ReprojectionLoss results: (SI, SI opted in, reproj, reproj opted in)."""
+        pred, gt, K = _f32(pred), _f32(gt), _f32(K)
+        B, _, H, W = pred.shape
+        out = (C.c_int * 4)()
+        err = C.create_string_buffer(2048)
+        if self.L.cadh_empty_rank(B, H, W, device, _p(pred), _p(gt), _p(K), out, err, len(err)):
+            self._raise(err)
+        return tuple(int(x) for x in out)
 
     def rays_roundtrip(self, device: int, K33, H: int, W: int, path: str, corrupt_dims: bool = False):
         """RayDirectionComputer::computeRayDirections -> saveRayDirections -> loadRayDirections (host/preprocessing).

@@ -99,6 +99,12 @@ inline cadl_results results_to_host(const torch::Tensor& results) {
     return r;
 }
 
+// the on-device cadl_results of this thread's most recent fused call (what the opt-in host reads look at)
+inline torch::Tensor& last_results() {
+    thread_local torch::Tensor t;
+    return t;
+}
+
 struct StackInputs {
     torch::Tensor pred, gt, rgb, K, mask;
     int B = 0, H = 0, W = 0;
@@ -119,6 +125,7 @@ inline torch::Tensor run_stack(const StackInputs& in, cadl_params p, torch::Tens
         reinterpret_cast<cadl_results*>(results.data_ptr<uint8_t>()), ws.data_ptr<uint8_t>(), ws_bytes,
         current_stream(dev));
     check_rc(rc, "cadl_stack_fwd_bwd");
+    last_results() = results;
     return results;
 }
 
@@ -215,6 +222,16 @@ struct PhotometricFunction : public torch::autograd::Function<PhotometricFunctio
         return {out, none, none, none, none, none, none, none};
     }
 };
+
+// The reference returns zeros(1) -- rank 1, no graph -- when no pixel is valid (depth_loss.h:53-55, 325-327), which it
+// learns from masked_select().numel(): a host sync.  The drop-in's default keeps the step free of syncs (0-dim result,
+// value 0, zero gradient); a caller that wants the reference's rank too opts into that one 8-byte read.
+inline torch::Tensor with_reference_empty_rank(const torch::Tensor& loss, size_t count_offset, const torch::Tensor& like) {
+    torch::Tensor results = last_results();          // the block the call that produced `loss` just wrote (this thread)
+    TORCH_CHECK(results.defined(), "cadl: loss tensor without its result block");
+    const int64_t n = results.narrow(0, (int64_t)count_offset, 8).view(torch::kInt64).item<int64_t>();
+    return n == 0 ? torch::zeros(1, like.options().requires_grad(false)) : loss;
+}
 
 struct TermCall {
     cadl_params p;

@@ -369,6 +369,29 @@ int cadh_photometric_step(int B, int H, int W, int device, const float* pred, co
     }
 }
 
+// Ranks of ScaleInvariantLoss / ReprojectionLoss on a batch (out4 = {SI default, SI opted in, reproj default, reproj
+// opted in}: dim() of the returned tensor; the reference gives 1 when no pixel is valid, 0 otherwise)
+int cadh_empty_rank(int B, int H, int W, int device, const float* pred, const float* gt, const float* K, int out4[4], char* err,
+                    int errlen) {
+    try {
+        auto dev = pick_device(device);
+        auto p = host_view(pred, {B, 1, H, W}).to(dev).clone().set_requires_grad(true);
+        auto g = host_view(gt, {B, 1, H, W}).to(dev);
+        auto k = host_view(K, {B, 3, 3}).to(dev);
+        ScaleInvariantLoss si, si2;
+        ReprojectionLoss rp, rp2;
+        si2.referenceEmptyRank(true);
+        rp2.referenceEmptyRank(true);
+        out4[0] = (int)si.forward(p, g).dim();
+        out4[1] = (int)si2.forward(p, g).dim();
+        out4[2] = (int)rp.forward(p, g, k).dim();
+        out4[3] = (int)rp2.forward(p, g, k).dim();
+        return 0;
+    } catch (const std::exception& e) {
+        return fail(err, errlen, e);
+    }
+}
+
 // RayDirectionComputer drop-in: rays of ONE camera on the device -> saveRayDirections -> loadRayDirections.
 // out_rays: H*W*3 floats as loaded back; returns the save() result in *saved (0: the reference's "false" paths).
 int cadh_rays_roundtrip(int device, int H, int W, const float* K9, const char* path, int corrupt_dims, float* out_rays,

@@ -11,7 +11,8 @@
 // Deliberate differences:
 //   * CUDA tensors only.  A CPU tensor raises c10::Error; there is no fallback.
 //   * ScaleInvariantLoss / ReprojectionLoss return a 0-dim tensor also when no pixel is valid (the
-//     reference returns zeros(1) there, depth_loss.h:53-55,325-327, at the price of a host sync).
+//     reference returns zeros(1) there, depth_loss.h:53-55,325-327, at the price of a host sync);
+//     referenceEmptyRank(true) on either object opts into that sync and the rank-1 zeros.
 #ifndef DEPTH_LOSS_H
 #define DEPTH_LOSS_H
 
@@ -40,8 +41,12 @@ public:
         cadl_params p;
         cadl_default_params(&p);
         p.terms = CADL_TERM_SI; p.w_si = 1.0f; p.si_lambda = lambda_; p.eps_si = eps_;
-        return apply_fused(pred, gt, torch::Tensor(), torch::Tensor(), mask, p, offsetof(cadl_results, loss_si));
+        auto loss = apply_fused(pred, gt, torch::Tensor(), torch::Tensor(), mask, p, offsetof(cadl_results, loss_si));
+        return sync_empty_ ? with_reference_empty_rank(loss, offsetof(cadl_results, n_si), pred) : loss;
     }
+
+    /// opt in to the reference's zeros(1) when no pixel is valid (depth_loss.h:53-55): costs one host sync per call
+    ScaleInvariantLoss& referenceEmptyRank(bool on) { sync_empty_ = on; return *this; }
 
     float lambda() const { return lambda_; }
     float eps() const { return eps_; }
@@ -49,6 +54,7 @@ public:
 private:
     float lambda_;
     float eps_;
+    bool sync_empty_ = false;
 };
 
 /// Multi-scale gradient matching in log depth (avg-pool pyramid, forward differences, L1).
@@ -123,8 +129,12 @@ public:
         cadl_params p;
         cadl_default_params(&p);
         p.terms = CADL_TERM_REPROJ; p.w_reproj = 1.0f; p.eps_reproj = eps_; p.k_batched = batched;
-        return apply_fused(pred, gt, torch::Tensor(), K, mask, p, offsetof(cadl_results, loss_reproj));
+        auto loss = apply_fused(pred, gt, torch::Tensor(), K, mask, p, offsetof(cadl_results, loss_reproj));
+        return sync_empty_ ? with_reference_empty_rank(loss, offsetof(cadl_results, n_reproj), pred) : loss;
     }
+
+    /// opt in to the reference's zeros(1) when no pixel is valid (depth_loss.h:325-327): costs one host sync per call
+    ReprojectionLoss& referenceEmptyRank(bool on) { sync_empty_ = on; return *this; }
 
     /// The reference's stub (depth_loss.h:343-351): zeros(1).  Kept verbatim in behaviour so callers
     /// see no change; the real warp is the opt-in forwardPhotometricWarp below.
@@ -161,6 +171,7 @@ public:
 
 private:
     float eps_;
+    bool sync_empty_ = false;
 };
 
 /// Weighted sum of the four terms.  reference: depth_loss.h:366-479

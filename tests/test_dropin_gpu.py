@@ -228,3 +228,13 @@ def test_reference_test_program_behaves_the_same_on_the_dropin():
     assert res_o["Scale-Invariant Loss"][1] == res_r["Scale-Invariant Loss"][1] == "Loss should be scalar"
     assert res_o["Smoothness Loss"][1] == res_r["Smoothness Loss"][1]
     assert rc_r == rc_o == 1
+
+
+def test_empty_mask_rank_is_the_reference_rank_when_opted_in(pkg, host):
+    """No valid pixel: the reference returns zeros(1) (rank 1; depth_loss.h:53-55, 325-327) because masked_select told
+    it so on the host.  The drop-in's default stays sync-free (0-dim zero); referenceEmptyRank(true) buys the rank back
+    with one 8-byte read.  With valid pixels both forms return 0-dim, like the reference."""
+    b = pkg.synth.make_batch(2, 32, 48, seed=3)
+    z = {k: v.numpy() for k, v in b.items()}
+    assert host.empty_rank(0, z["pred"], np.zeros_like(z["gt"]), z["K"]) == (0, 1, 0, 1)
+    assert host.empty_rank(0, z["pred"], z["gt"], z["K"]) == (0, 0, 0, 0)

@@ -425,7 +425,13 @@ cudaError_t launch_point(const PhaseBArgs& a, cudaStream_t st) {
 StepPlan concurrent_plan(const Ws& ws, int B, bool metrics) {
     StepPlan plan;
     const int sms = num_sms_cached();
-    const int pyr_ctas = (metrics ? 2 : 3) * sms;
+#ifndef CADL_PLAN_M
+#define CADL_PLAN_M 2
+#endif
+#ifndef CADL_PLAN_N
+#define CADL_PLAN_N 3
+#endif
+    const int pyr_ctas = (metrics ? CADL_PLAN_M : CADL_PLAN_N) * sms;
     plan.pyr_grid = ws.L.pyr_blocks < pyr_ctas ? ws.L.pyr_blocks : pyr_ctas;
     plan.a_blocks_per_img = (4 * sms - plan.pyr_grid) / B;       // phase A: 4 CTAs of 256 threads per SM
     if (plan.a_blocks_per_img < 1) plan.a_blocks_per_img = 1;

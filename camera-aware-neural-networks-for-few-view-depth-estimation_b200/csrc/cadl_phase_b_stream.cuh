@@ -30,7 +30,10 @@ struct PyrArrays {
 // ================================================================================================
 // pyr_pool_kernel
 // ================================================================================================
-__global__ void __launch_bounds__(256) pyr_pool_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+#ifndef CADL_PYR_MINB
+#define CADL_PYR_MINB 4
+#endif
+__global__ void __launch_bounds__(256, CADL_PYR_MINB) pyr_pool_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
                                                        int B, int H, int W, float eps, PyrArrays py,
                                                        unsigned int* img_rec_words) {
     // Launched with programmatic stream serialization behind phase A, of which it needs nothing: it starts as
@@ -192,7 +195,7 @@ struct PyrCoefArgs {
     int row0;           // first row this kernel writes
 };
 
-__global__ void __launch_bounds__(256) pyr_coef_kernel(const PyrCoefArgs a) {
+__global__ void __launch_bounds__(256, CADL_PYR_MINB) pyr_coef_kernel(const PyrCoefArgs a) {
     __shared__ float s_f[8][6];
     pdl_wait();        // the pooled arrays of pyr_pool_kernel
     pdl_trigger();

@@ -146,8 +146,9 @@ __device__ __noinline__ float4 div4_ieee(float a, float b, float c, float d, flo
 // One image row as a lane holds it in registers.
 struct Row3 {
     float4 p, g;        // pred, gt (4 adjacent pixels)
-    float4 I[3];        // rgb
     float d[4];         // lg2(clamp(pred)) - lg2(clamp(gt))     depth_loss.h:115-116 (log2 units)
+    // (the rgb values are NOT kept: each use reads them from the row's ring slot again -- 24 registers less per thread,
+    //  which is what lets a fourth CTA of 128 threads onto the SM)
 };
 
 template <int F, bool HAS_MASK>
@@ -272,10 +273,6 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
             const float* q = myq + s * (SLOT);
             R.p = *reinterpret_cast<const float4*>(q);
             R.g = *reinterpret_cast<const float4*>(q + kS3RowFloats);
-            if constexpr (SMOOTH) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) R.I[c] = *reinterpret_cast<const float4*>(q + (2 + c) * kS3RowFloats);
-            }
             const float pv[4] = {R.p.x, R.p.y, R.p.z, R.p.w}, gv[4] = {R.g.x, R.g.y, R.g.z, R.g.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -296,7 +293,7 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
         // sys: signed magnitude of d loss_0 / d e_y; tys: same for the smoothness term; flag: a residual inside the
         // band or a NaN -> the exact tier decides (a depth step that is exactly zero -- saturated predictions -- is
         // common and handled in line)
-        auto yedges = [&](const Row3& C, const Row3& N, float (&sys)[4], float (&tys)[4], bool& flag) {
+        auto yedges = [&](const Row3& C, const Row3& N, const float* cI, const float* nI, float (&sys)[4], float (&tys)[4], bool& flag) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float e = N.d[k] - C.d[k];                              // depth_loss.h:151-163
@@ -313,8 +310,8 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
                     float2 s = make_float2(0.f, 0.f);
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        const float2 ci = h ? make_float2(C.I[c].z, C.I[c].w) : make_float2(C.I[c].x, C.I[c].y);
-                        const float2 ni = h ? make_float2(N.I[c].z, N.I[c].w) : make_float2(N.I[c].x, N.I[c].y);
+                        const float2 ci = *reinterpret_cast<const float2*>(cI + (2 + c) * kS3RowFloats + 2 * h);
+                        const float2 ni = *reinterpret_cast<const float2*>(nI + (2 + c) * kS3RowFloats + 2 * h);
                         const float2 di = __fadd2_rn(ni, neg2(ci));
                         s = __fadd2_rn(s, make_float2(fabsf(di.x), fabsf(di.y)));     // depth_loss.h:218-227
                     }
@@ -379,7 +376,8 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
                 float Ix[3][5], Il[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    Ix[c][0] = C.I[c].x; Ix[c][1] = C.I[c].y; Ix[c][2] = C.I[c].z; Ix[c][3] = C.I[c].w;
+                    const float4 v = *reinterpret_cast<const float4*>(cq + (2 + c) * kS3RowFloats);
+                    Ix[c][0] = v.x; Ix[c][1] = v.y; Ix[c][2] = v.z; Ix[c][3] = v.w;
                     Ix[c][4] = cq[(2 + c) * kS3RowFloats + 4];
                     Il[c] = cq[(2 + c) * kS3RowFloats - 1];
                 }
@@ -393,7 +391,7 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
                     flag |= (dpx != dpx);
                 }
                 {   // lane 0: the edge to its left neighbour
-                    const float s = fabsf(C.I[0].x - Il[0]) + fabsf(C.I[1].x - Il[1]) + fabsf(C.I[2].x - Il[2]);
+                    const float s = fabsf(Ix[0][0] - Il[0]) + fabsf(Ix[1][0] - Il[1]) + fabsf(Ix[2][0] - Il[2]);
                     const float wl = ex2_approx(fmaf(s, kExpScale, lsnl));
                     const float dl = cp[0] - pl;
                     tx[0] = with_sign0(wl, dl);
@@ -459,7 +457,7 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
             // 4. the next row: wait for its slot, its log differences, the vertical edges
             wait_slot(sn);
             read_row(sn, N);
-            yedges(C, N, sy_dn, ty_dn, flag);
+            yedges(C, N, cq, myq + sn * (SLOT), sy_dn, ty_dn, flag);
 
             // 5. exact tier, warp-uniform and rare (about 1 % of the warp-rows on BASELINE's data)
             if (__any_sync(0xffffffffu, flag)) {
@@ -510,7 +508,7 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
             bool flag = false;
             const float k_gy = sg_gy;
             const float2 k_smy = sg_smy;
-            yedges(RB, RA, u0s, u0t, flag);
+            yedges(RB, RA, myq, myq + SLOT, u0s, u0t, flag);
             sg_gy = k_gy; sg_smy = k_smy;                    // that edge is counted by the share above
             if (__any_sync(0xffffffffu, flag)) {
                 const ExactSigns x = exact_tier<SMOOTH>(RB.p, RB.g, 1.f, 1.f, 1.f, 1.f, RA.p, RA.g, eps);

@@ -12,7 +12,7 @@ for spec in "$@"; do
   src="${S2SRC:-cadl_stream3.cu}"
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -I../../include $flags \
        -c -o variants/${src%.cu}_$tag.o $src -Xptxas -v 2> variants/$tag.ptxas.log
-  objs=$(ls obj/*.o | grep -v "${src%.cu}.o")
+  objs=$(ls obj/*.o | grep -v "${src%.cu}.o" | grep -v "_dbg.o")
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -o variants/libcadl_$tag.so $objs variants/${src%.cu}_$tag.o
   echo "built variants/libcadl_$tag.so ($flags)"
 done

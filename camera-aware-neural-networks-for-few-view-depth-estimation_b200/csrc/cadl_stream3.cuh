@@ -703,8 +703,18 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
             const float noff = -off;
             const int gx0 = strip * 128 + 4 * lane;
             if (gx0 < W) {
+                // (four independent address registers per trip: a reduction holds its address until it has left the SM)
                 float* gp = a.grad + (b * plane + ys * W + gx0);
-                for (int y = ys; y < ye; ++y) {
+                int y = ys;
+                for (; y + 4 <= ye; y += 4) {
+                    float* g0 = gp; float* g1 = gp + W; float* g2 = gp + 2 * W; float* g3 = gp + 3 * W;
+                    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %1, %1, %1};" :: "l"(g0), "f"(noff) : "memory");
+                    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %1, %1, %1};" :: "l"(g1), "f"(noff) : "memory");
+                    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %1, %1, %1};" :: "l"(g2), "f"(noff) : "memory");
+                    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %1, %1, %1};" :: "l"(g3), "f"(noff) : "memory");
+                    gp += 4 * W;
+                }
+                for (; y < ye; ++y) {
                     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %1, %1, %1};" :: "l"(gp), "f"(noff) : "memory");
                     gp += W;
                 }

@@ -976,8 +976,7 @@ int cadl_stats_exchange(void* workspace, void* const* inboxes_host, int rank, in
     a.rank = rank; a.world = world; a.epoch = epoch;
     a.timeout_ns = (unsigned long long)((timeout_s > 0.0 ? timeout_s : 600.0) * 1e9);
     a.error = reinterpret_cast<int*>(a.inbox[rank] + 2 * (size_t)world * kP2PSlotDoubles);
-    stats_exchange_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(a);
-    return cuda_rc(cudaGetLastError());
+    return cuda_rc(launch_pdl(stats_exchange_kernel, dim3(1), dim3(64), (cudaStream_t)stream, !g_no_pdl, a));
 }
 
 int cadl_p2p_error(void* own_inbox_dev, int world, int* error_host, int clear) {

@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(64) stats_exchange_kernel(const P2PArgs a) {
     __shared__ int s_timeout;
     const int t = threadIdx.x;
     if (t == 0) s_timeout = 0;
+    pdl_wait();        // launched with programmatic stream serialization behind phase A: its statistics
     const size_t slot = ((size_t)(a.epoch & 1ull) * a.world + a.rank) * kP2PSlotDoubles;
     if (t < ST_COUNT) {
         const double v = a.stats[t];

@@ -286,7 +286,8 @@ def force_generic(on):
     """Test hook (bit mask, see include/cadl.h under CADL_DEBUG): a non-zero mode routes every following call through
     libcadl_dbg.so with that dispatch (1 = generic phase-B kernel, 8 = one tile kernel instead of the pyramid +
     streaming kernels, 8|2 = that kernel staged with cp.async, 16 = no programmatic dependent launch, 32 = pyramid
-    kernels in line, 64 = reprojection alone with the separate count kernel); 0 returns to the product library."""
+    kernels in line, 64 = reprojection alone with the separate count kernel, 128 = loss statistics from phase A instead
+    of the pooled-sum pass); 0 returns to the product library."""
     global _active
     on = int(on)
     if on:

@@ -90,6 +90,7 @@ struct Ws {
     double* img_sm() const { return reinterpret_cast<double*>(base + L.img_sm); }
     float* img_off() const { return reinterpret_cast<float*>(base + L.img_off); }
     ImgRec* img_rec() const { return reinterpret_cast<ImgRec*>(base + L.img_rec); }
+    unsigned long long* img_words() const { return reinterpret_cast<unsigned long long*>(base + L.img_words); }
     bool has_pyr() const { return L.pyr_blocks > 0; }
     PyrArrays pyr() const {
         PyrArrays p;
@@ -113,6 +114,7 @@ int g_force_tile = 0;       // bit 3: the one-CTA-per-tile fast kernel instead o
 int g_no_pdl = 0;           // bit 4: plain stream-ordered launches (no programmatic dependent launch)
 int g_no_overlap = 0;       // bit 5: pooled-pyramid kernels in line on the caller's stream instead of beside phase A
 int g_no_coop = 0;          // bit 6: reprojection alone keeps the separate count kernel (no cooperative launch)
+int g_no_poolstats = 0;     // bit 7: the loss statistics from phase A (the split API's kernels) instead of the pooled-sum pass
 // cadl_debug_kernel_times: CUDA events between the launches of one cadl_stack_fwd_bwd call
 struct KTimes {
     bool on = false;
@@ -141,7 +143,7 @@ void kt_finish() {
 }
 inline bool kt_on() { return g_kt.on; }
 #else
-constexpr int g_force_generic = 0, g_force_no_tma = 0, g_force_tile = 0, g_no_pdl = 0, g_no_overlap = 0, g_no_coop = 0;
+constexpr int g_force_generic = 0, g_force_no_tma = 0, g_force_tile = 0, g_no_pdl = 0, g_no_overlap = 0, g_no_coop = 0, g_no_poolstats = 0;
 inline void kt_mark(cudaStream_t, const char*) {}
 inline void kt_finish() {}
 inline bool kt_on() { return false; }
@@ -293,6 +295,7 @@ int num_sms_cached() {         // of the CURRENT device (a process may drive sev
 
 // How one cadl_stack_fwd_bwd call is laid out over launches (decided once, used by the reduce and the gradient part).
 struct StepPlan {
+    int pool_stats = 0;             // PS_* bits: the pooled-sum kernel also produces the loss statistics (no phase A for them)
     bool pyr_prelaunched = false;   // the pooled-pyramid kernels already run on the auxiliary stream, beside phase A
     int pyr_grid = 0;               // CTAs (= partial rows) of pyr_coef_kernel; 0 = one thread per 8x8 block
     int a_blocks_per_img = 0;       // phase A grid override (0 = the workspace layout's)
@@ -320,17 +323,29 @@ AuxStream* aux_for_current_device() {
     return &x;
 }
 
-cudaError_t launch_pyramid(const PhaseBArgs& a, const Ws& ws, cudaStream_t st, int grid, bool pdl_pool, bool pdl) {
+cudaError_t launch_pyramid(const PhaseBArgs& a, const Ws& ws, cudaStream_t st, int grid, bool pdl_pool, bool pdl, int pool_stats = 0) {
     const PyrArrays py = ws.pyr();
-    cudaError_t e = launch_pdl(pyr_pool_kernel, dim3(grid), dim3(256), st, pdl_pool, a.pred, a.gt, a.B, a.H, a.W, a.eps_grad, py,
-                               reinterpret_cast<unsigned int*>(ws.img_rec()));
+    PoolStatsArgs ps{};
+    cudaError_t e;
+    unsigned int* recs = reinterpret_cast<unsigned int*>(ws.img_rec());
+    if (pool_stats) {
+        // the statistics of the loss terms ride on the pooled-sum pass (eps_si == eps_rp == eps_grad on this path)
+        ps.mask = a.mask; ps.rec = reinterpret_cast<PoolStatsRec*>(ws.hdr()->pool_rec); ps.img_words = ws.img_words();
+        ps.stats = ws.stats(); ps.img_psum = ws.img_psum(); ps.want_rp = (a.terms & CADL_TERM_REPROJ) ? 1 : 0;
+        if (a.mask)
+            e = launch_pdl(pyr_pool_kernel<PS_SI | PS_PSUM, true>, dim3(grid), dim3(256), st, pdl_pool, a.pred, a.gt, a.B, a.H, a.W, a.eps_grad, py, recs, ps);
+        else
+            e = launch_pdl(pyr_pool_kernel<PS_SI | PS_PSUM, false>, dim3(grid), dim3(256), st, pdl_pool, a.pred, a.gt, a.B, a.H, a.W, a.eps_grad, py, recs, ps);
+    } else {
+        e = launch_pdl(pyr_pool_kernel<0, false>, dim3(grid), dim3(256), st, pdl_pool, a.pred, a.gt, a.B, a.H, a.W, a.eps_grad, py, recs, ps);
+    }
     if (e != cudaSuccess) return e;
     kt_mark(st, "pyr_pool_kernel");
     PyrCoefArgs ca{};
     ca.py = py; ca.B = a.B; ca.H = a.H; ca.W = a.W;
     for (int s = 0; s < 4; ++s) { ca.inv_nx[s] = a.inv_nx[s]; ca.inv_ny[s] = a.inv_ny[s]; }
     ca.wg = 0.25f * a.w_grad * a.upstream;          // 1/num_scales * weight * upstream
-    ca.b_part = a.b_part; ca.row0 = a.B;             // final rows: [B per-image rows][one row per CTA of this kernel]
+    ca.rec = reinterpret_cast<unsigned long long*>(ws.img_rec() + a.B);      // the record behind the B image records
     e = launch_pdl(pyr_coef_kernel, dim3(grid), dim3(256), st, pdl, ca);
     if (e != cudaSuccess) return e;
     kt_mark(st, "pyr_coef_kernel");
@@ -350,13 +365,13 @@ cudaError_t launch_stream(PhaseBArgs& a, const Ws& ws, cudaStream_t st, bool* of
     if (!(a.eps_grad >= 1e-30f && (!(F & FB_SI) || a.eps_si == a.eps_grad) && (!(F & FB_RP) || a.eps_rp == a.eps_grad)))
         return cudaErrorNotSupported;
     if (!plan.pyr_prelaunched) {
-        e = launch_pyramid(a, ws, st, nblk, pdl, pdl);
+        e = launch_pyramid(a, ws, st, nblk, pdl, pdl, plan.pool_stats);
         if (e != cudaSuccess) return e;
     }
     // TMA row ring, two-tier logs, packed reprojection, smoothness offset applied in-kernel (cadl_stream3.cuh)
     Stream3Args s3{};
     s3.c1 = py.c1; s3.nstrip = (a.W + 127) / 128;
-    s3.pyr_rows = a.b_part + (size_t)a.B * BF_COUNT; s3.n_pyr_rows = nblk;
+    s3.pyr_rec = reinterpret_cast<const unsigned long long*>(ws.img_rec() + a.B);
     s3.img = ws.img_rec(); s3.done = &ws.hdr()->ticket_b; s3.epoch = &ws.hdr()->pad[0];
     if ((F & FB_SMOOTH) && !stream3_fill_smooth(a, s3)) return cudaErrorNotSupported;
     e = launch_stream3(F, a, s3, st);
@@ -422,6 +437,11 @@ cudaError_t launch_point(const PhaseBArgs& a, cudaStream_t st) {
 // metrics (the trainers' step) phase A is short and the pyramid gets 3 per SM (296: 177.1, 370: 169.3, 444: 166.1,
 // 518: 189.9; in line 174.8).  Everything must fit ONE wave: more, shorter phase-A blocks starve the pyramid (13
 // blocks per image 207.0 us/step, 18: 204.8, 36: 208.7 against 9: 196.5).
+// CTAs of 256 threads per SM of the pooled-sum / coefficient kernels in the step without a phase A (cadl_stack_fwd_bwd;
+// 2: 116 us/step, 3, 4, 5: 108-109)
+#ifndef CADL_PLAN2_PYR_N
+#define CADL_PLAN2_PYR_N 4
+#endif
 StepPlan concurrent_plan(const Ws& ws, int B, bool metrics) {
     StepPlan plan;
     const int sms = num_sms_cached();
@@ -669,6 +689,7 @@ void cadl_debug_force_generic(int on) {
     g_no_pdl = (on >> 4) & 1;
     g_no_overlap = (on >> 5) & 1;
     g_no_coop = (on >> 6) & 1;
+    g_no_poolstats = (on >> 7) & 1;
 }
 #endif
 size_t cadl_sizeof_params(void) { return sizeof(cadl_params); }
@@ -785,6 +806,27 @@ int cadl_stack_fwd_bwd(const float* pred, const float* gt, const float* rgb, con
     // persistent CTA per SM; phase A follows on the caller's stream with a grid that leaves them room.
     StepPlan plan;
     AuxStream* aux = nullptr;
+    // Streaming path with the SI and smoothness terms and no metric variant (the trainers' training step): NO phase A.
+    // The pooled-sum kernel reads every pred/gt value anyway and produces SI n / sum d / sum d^2 and the per-image
+    // sum(pred) on its way: pool + statistics -> coefficients -> gradient pass, three launches on the caller's stream
+    // (config 3 without metrics: 108 us/step against 120 with phase A beside the pyramid kernels).  With metric variants
+    // phase A has to run anyway and carries the loss statistics at no extra cost, so that step keeps the layout below
+    // (measured: a metrics-only phase A beside the new chain 130-150 us/step depending on how the two streams' CTAs
+    // interleave, behind the gradient pass with programmatic serialization 153, the layout below 128).
+    if (!g_no_overlap && !g_no_poolstats && !kt_on() && results && params->metrics == 0) {
+        PhaseBArgs a;
+        bool nothing = false;
+        const uint32_t t = params->terms & CADL_TERM_ALL;
+        if ((t == CADL_TERM_ALL || t == (CADL_TERM_SI | CADL_TERM_GRAD | CADL_TERM_SMOOTH)) &&
+            fill_b_args(a, pred, gt, rgb, K, mask, B, H, W, *params, grad_pred, results, ws, &nothing) == CADL_OK && !nothing &&
+            stream_path_ok(a, *params, ws) && params->eps_si == params->eps_grad &&
+            (!(t & CADL_TERM_REPROJ) || params->eps_reproj == params->eps_grad) && (!mask || aligned(mask, 8))) {
+            plan.pool_stats = PS_SI | PS_PSUM;
+            plan.pyr_grid = CADL_PLAN2_PYR_N * num_sms_cached();
+            if (plan.pyr_grid > ws.L.pyr_blocks) plan.pyr_grid = ws.L.pyr_blocks;
+            return run_grad(pred, gt, rgb, K, mask, B, H, W, *params, grad_pred, results, ws, st, plan);
+        }
+    }
     if (!g_no_overlap && !kt_on() && phase_a_flags(*params) != 0 && results) {
         PhaseBArgs a;
         bool nothing = false;

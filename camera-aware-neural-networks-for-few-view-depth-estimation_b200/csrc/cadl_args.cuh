@@ -80,45 +80,6 @@ __device__ __forceinline__ void smooth_image_share(const PhaseBArgs& a, int img,
     off = (float)((double)a.upstream * a.w_smooth * ab * Lb / HW);
 }
 
-// Metrics results from the phase-A statistics (depth_metrics.h:69-85; trainer :418-436).  Called by at least 32
-// threads with t = thread index: one value per thread (a single thread doing the ~25 double divisions one after
-// the other was ~4 us of serial tail).
-__device__ inline void write_metric_results(const double* st, uint32_t which, cadl_results& r, int t) {
-    if (which & CADL_METRICS_EVAL) {
-        const double n = st[ST_EV_N];
-        if (t < 12) {
-            // getZeroMetrics when nothing is valid, depth_metrics.h:238-253
-            const int src = t == 0 ? ST_EV_ABSREL : t == 1 ? ST_EV_SQREL : t == 2 ? ST_EV_SQ : t == 3 ? ST_EV_LOGSQ
-                          : t == 4 ? ST_EV_ABS : t == 5 ? ST_EV_LOG10 : t == 6 ? ST_EV_C1 : t == 7 ? ST_EV_C2
-                          : t == 8 ? ST_EV_C3 : t == 10 ? ST_EV_SUMP : ST_EV_SUMG;
-            float v = 0.f;
-            if (n > 0.0) {
-                if (t == 9) v = (float)n;                                  // static_cast<float>(num_valid), :83
-                else if (t == 2 || t == 3) v = sqrtf((float)(st[src] / n));
-                else v = (float)(st[src] / n);
-            }
-            r.eval[t] = v;
-        } else if (t < 16) {
-            const int k = t - 12;
-            r.eval_counts[k] = (int64_t)st[k == 0 ? ST_EV_N : ST_EV_C1 + (k - 1)];
-        }
-    }
-    if (which & CADL_METRICS_TRAIN) {
-        const double n = st[ST_TR_N];
-        if (t >= 16 && t < 24) {
-            const int k = t - 16;
-            const int src = k == 0 ? ST_TR_ABSREL : k == 1 ? ST_TR_SQREL : k == 2 ? ST_TR_SQ : k == 3 ? ST_TR_LOGSQ
-                          : k == 4 ? ST_TR_C1 : k == 5 ? ST_TR_C2 : ST_TR_C3;
-            float v = 0.f;
-            if (n > 0.0 && k < 7) v = (k == 2 || k == 3) ? sqrtf((float)(st[src] / n)) : (float)(st[src] / n);
-            r.train[k] = v;
-        } else if (t >= 24 && t < 28) {
-            const int k = t - 24;
-            r.train_counts[k] = (int64_t)st[k == 0 ? ST_TR_N : ST_TR_C1 + (k - 1)];
-        }
-    }
-}
-
 __device__ __forceinline__ void load_K(const PhaseBArgs& a, int b, float& fx, float& fy, float& cx,
                                        float& cy) {
     const float* Kb = a.K + (a.k_batched ? (size_t)b * 9 : 0);

@@ -49,10 +49,11 @@ struct WsHeader {
     unsigned int ticket_b;
     unsigned int pad[2];
     unsigned long long icount[16];
+    unsigned long long pool_rec[8];     // PoolStatsRec (cadl_phase_b_stream.cuh): fixed offset, zero between calls
 };
 
 struct WsLayout {
-    size_t header, stats, img_psum, a_part, b_part, img_sm, img_off, img_rec, total;
+    size_t header, stats, img_words, img_psum, a_part, b_part, img_sm, img_off, img_rec, total;
     size_t pyr_lp[3], pyr_lg[3], pyr_rq[3], pyr_c1;   // streaming fast path (cadl_phase_b_stream.cuh); 0 = absent
     int a_blocks_per_img, a_blocks, b_tiles;
     int pyr_blocks;   // CTAs of pyr_pool_kernel / pyr_coef_kernel (0: shape not a multiple of 8)
@@ -88,6 +89,7 @@ __host__ inline WsLayout ws_layout(int B, int H, int W) {
     size_t o = 0;
     L.header = o;   o = align_up(o + sizeof(WsHeader), 256);
     L.stats = o;    o = align_up(o + sizeof(double) * ST_COUNT, 256);
+    L.img_words = o; o = align_up(o + 32 * (size_t)B, 256);                    // pyr_pool_kernel's per-image fixed-point words (fixed offset; zero between calls)
     L.img_psum = o; o = align_up(o + sizeof(double) * B, 256);
     L.a_part = o;   o = align_up(o + sizeof(double) * (size_t)L.a_blocks * AF_COUNT, 256);
     const bool pyr = (H % 8 == 0) && (W % 8 == 0);
@@ -99,7 +101,7 @@ __host__ inline WsLayout ws_layout(int B, int H, int W) {
     L.b_part = o;   o = align_up(o + sizeof(double) * b_rows * BF_COUNT, 256);
     L.img_sm = o;   o = align_up(o + sizeof(double) * (size_t)B * 2, 256);
     L.img_off = o;  o = align_up(o + sizeof(float) * (size_t)B, 256);
-    L.img_rec = o;  o = align_up(o + 128 * (size_t)B, 256);                    // ImgRec per image (cadl_stream3_host.h)
+    L.img_rec = o;  o = align_up(o + 128 * ((size_t)B + 1), 256);              // ImgRec per image (cadl_stream3_host.h) + pyr_coef_kernel's totals
     for (int s = 0; s < 3; ++s) {
         const size_t cells = pyr ? (size_t)B * (H >> (s + 1)) * (W >> (s + 1)) : 0;
         L.pyr_lp[s] = pyr ? o : 0; o = align_up(o + sizeof(float) * cells, 256);
@@ -141,6 +143,45 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
+}
+
+// Metrics results from the phase-A statistics (depth_metrics.h:69-85; trainer :418-436).  Called by at least 32
+// threads with t = thread index: one value per thread (a single thread doing the ~25 double divisions one after
+// the other was ~4 us of serial tail).
+__device__ inline void write_metric_results(const double* st, uint32_t which, cadl_results& r, int t) {
+    if (which & CADL_METRICS_EVAL) {
+        const double n = st[ST_EV_N];
+        if (t < 12) {
+            // getZeroMetrics when nothing is valid, depth_metrics.h:238-253
+            const int src = t == 0 ? ST_EV_ABSREL : t == 1 ? ST_EV_SQREL : t == 2 ? ST_EV_SQ : t == 3 ? ST_EV_LOGSQ
+                          : t == 4 ? ST_EV_ABS : t == 5 ? ST_EV_LOG10 : t == 6 ? ST_EV_C1 : t == 7 ? ST_EV_C2
+                          : t == 8 ? ST_EV_C3 : t == 10 ? ST_EV_SUMP : ST_EV_SUMG;
+            float v = 0.f;
+            if (n > 0.0) {
+                if (t == 9) v = (float)n;                                  // static_cast<float>(num_valid), :83
+                else if (t == 2 || t == 3) v = sqrtf((float)(st[src] / n));
+                else v = (float)(st[src] / n);
+            }
+            r.eval[t] = v;
+        } else if (t < 16) {
+            const int k = t - 12;
+            r.eval_counts[k] = (int64_t)st[k == 0 ? ST_EV_N : ST_EV_C1 + (k - 1)];
+        }
+    }
+    if (which & CADL_METRICS_TRAIN) {
+        const double n = st[ST_TR_N];
+        if (t >= 16 && t < 24) {
+            const int k = t - 16;
+            const int src = k == 0 ? ST_TR_ABSREL : k == 1 ? ST_TR_SQREL : k == 2 ? ST_TR_SQ : k == 3 ? ST_TR_LOGSQ
+                          : k == 4 ? ST_TR_C1 : k == 5 ? ST_TR_C2 : ST_TR_C3;
+            float v = 0.f;
+            if (n > 0.0 && k < 7) v = (k == 2 || k == 3) ? sqrtf((float)(st[src] / n)) : (float)(st[src] / n);
+            r.train[k] = v;
+        } else if (t >= 24 && t < 28) {
+            const int k = t - 24;
+            r.train_counts[k] = (int64_t)st[k == 0 ? ST_TR_N : ST_TR_C1 + (k - 1)];
+        }
+    }
 }
 
 }  // namespace cadl

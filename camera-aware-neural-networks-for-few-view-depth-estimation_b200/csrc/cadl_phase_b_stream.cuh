@@ -33,22 +33,65 @@ struct PyrArrays {
 #ifndef CADL_PYR_MINB
 #define CADL_PYR_MINB 4
 #endif
+// Statistics the pooled-sum pass can produce on its way (it reads every pred/gt value anyway): what phase A would
+// compute for the loss terms -- SI n / sum d / sum d^2 (the reprojection count is the same mask on this path) and the
+// per-image sum(pred) of the smoothness normaliser.  With them the loss step needs no phase A at all; the metric
+// variants, if asked for, run as a metrics-only phase A on the auxiliary stream (cadl_api.cu: cadl_stack_fwd_bwd).
+constexpr int PS_SI = 1, PS_PSUM = 2;
+struct PoolStatsRec {               // fixed offset in the workspace header; zero between calls
+    unsigned long long n;           // valid pixels                                   depth_loss.h:52, :323
+    unsigned long long s_hi, s_lo;  // sum d,   log2 units, signed fixed point        depth_loss.h:61
+    unsigned long long q_hi, q_lo;  // sum d^2, log2^2 units                          depth_loss.h:58
+    unsigned int ticket, flags;     // flags: fix_split bits of quantity 0 (s) and 1 (q)
+};
+struct PoolStatsArgs {
+    const uint8_t* mask;
+    PoolStatsRec* rec;
+    unsigned long long* img_words;  // per image: hi, lo, flags, pad (sum of pred, signed fixed point); zero between calls
+    double* stats;                  // ST_* vector: the last CTA writes ST_SI_N, ST_SI_S, ST_SI_Q (and ST_RP_N when want_rp)
+    double* img_psum;               // per-image sum(pred), written by the last CTA
+    int want_rp;
+};
+// signed variant of fix_split: hi is a two's-complement count of 2^-16 units (unsigned wrap-around addition is exact)
+__device__ __forceinline__ void fix_split_signed(double v, unsigned long long& hi, unsigned long long& lo, unsigned& flag, int q) {
+    hi = 0ull; lo = 0ull;
+    if (!(fabs(v) < 1.0e14)) { flag |= (v != v) ? (1u << q) : (v > 0.0 ? (1u << (8 + q)) : (1u << (16 + q))); return; }
+    const double sc = v * 65536.0, h = floor(sc);
+    hi = (unsigned long long)(long long)h;
+    lo = (unsigned long long)__double2ll_rn((sc - h) * 1099511627776.0);          // 2^40: lo in 2^-56 units
+}
+__device__ __forceinline__ double fix_join_signed(unsigned long long hi, unsigned long long lo, unsigned flags, int q) {
+    if (flags & (1u << q)) return __longlong_as_double(0x7ff8000000000000ll);
+    if ((flags & (1u << (8 + q))) && (flags & (1u << (16 + q)))) return __longlong_as_double(0x7ff8000000000000ll);   // inf - inf
+    if (flags & (1u << (8 + q))) return __longlong_as_double(0x7ff0000000000000ll);
+    if (flags & (1u << (16 + q))) return __longlong_as_double(0xfff0000000000000ll);
+    return (double)(long long)hi * (1.0 / 65536.0) + (double)lo * (1.0 / 72057594037927936.0);
+}
+
+template <int SF, bool HAS_MASK>
 __global__ void __launch_bounds__(256, CADL_PYR_MINB) pyr_pool_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
                                                        int B, int H, int W, float eps, PyrArrays py,
-                                                       unsigned int* img_rec_words) {
-    // Launched with programmatic stream serialization behind phase A, of which it needs nothing: it starts as
-    // phase A's CTAs drain.  It only has to END after phase A (pdl_wait below), so that the kernels behind it,
-    // which wait for THIS grid, also see phase A's statistics.
+                                                       unsigned int* img_rec_words, const PoolStatsArgs ps) {
+    // Launched with programmatic stream serialization: the pooling loop needs nothing from the kernel before it in the
+    // stream (the previous step's gradient pass or metrics pass, or phase A) and runs while that one drains.  Everything
+    // that kernel may still read or write -- the per-image records, the statistics -- is touched only behind the
+    // pdl_wait() below, which also makes this grid END after its predecessor: the kernels behind it wait for THIS grid.
     pdl_trigger();
     const int W8 = W >> 3, H8 = H >> 3;
-    // the streaming kernel's per-image records (stream-ordered before it; their offset depends on the shape, and one
-    // workspace serves calls of different shapes: what lies there may be another shape's partial sums)
-    if (blockIdx.x == 0)
-        for (int i = threadIdx.x; i < B * 32; i += blockDim.x) img_rec_words[i] = 0u;      // 128 bytes per image
+    unsigned si_n = 0u;
+    float si_s = 0.f, si_q = 0.f;
+    const int lane = threadIdx.x & 31;
+    const int total = B * H8 * W8;
     // grid-stride over the 8x8 blocks: the grid is either one thread per block or, when the kernel runs beside
     // phase A on a second stream, one CTA per SM
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < B * H8 * W8; idx += gridDim.x * blockDim.x) {
+    // (warp-uniform trips: with statistics the warp reduces its per-image sums together; a lane past the end works on
+    //  the last block again and neither stores nor counts)
+    for (int idx0 = blockIdx.x * blockDim.x + threadIdx.x - lane; idx0 < total; idx0 += gridDim.x * blockDim.x) {
+    const bool act = idx0 + lane < total;
+    if (SF == 0 && !act) break;
+    const int idx = act ? idx0 + lane : total - 1;
     const int bx = idx % W8, by = (idx / W8) % H8, b = idx / (W8 * H8);
+    float bsum = 0.f;
     const float* pp = pred + (size_t)b * H * W + (size_t)(by * 8) * W + bx * 8;
     const float* gp = gt + (size_t)b * H * W + (size_t)(by * 8) * W + bx * 8;
     const int W1 = W >> 1, W2 = W >> 2, W3 = W >> 3, H1 = H >> 1, H2 = H >> 2, H3 = H >> 3;
@@ -62,6 +105,22 @@ __global__ void __launch_bounds__(256, CADL_PYR_MINB) pyr_pool_kernel(const floa
         const float4 gb = __ldg(reinterpret_cast<const float4*>(gp + (size_t)r * W + 4));
         const float vp[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
         const float vg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+        if constexpr (SF != 0) {
+            unsigned long long mbits = 0ull;
+            if constexpr (HAS_MASK) mbits = __ldg(reinterpret_cast<const unsigned long long*>(ps.mask + (size_t)b * H * W + (size_t)(by * 8 + r) * W + bx * 8));
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if constexpr (SF & PS_PSUM) bsum += vp[c];                                  // depth_loss.h:192
+                if constexpr (SF & PS_SI) {                                                 // depth_loss.h:38-47 (phase_a_px)
+                    const bool m = (HAS_MASK ? ((mbits >> (8 * c)) & 0xffull) != 0ull : (vg[c] > eps)) && act;
+                    const float d2 = lg2_approx(clamp_nan(vp[c], eps, 1000.0f)) - lg2_approx(clamp_nan(vg[c], eps, 1000.0f));
+                    const float d = m ? d2 : 0.f;
+                    si_n += m ? 1u : 0u;
+                    si_s += d;
+                    si_q = fmaf(d, d, si_q);
+                }
+            }
+        }
         // running window sums, row-major sequential inside each window (ATen avg_pool2d order)
         if ((r & 1) == 0) {
 #pragma unroll
@@ -86,31 +145,116 @@ __global__ void __launch_bounds__(256, CADL_PYR_MINB) pyr_pool_kernel(const floa
 #pragma unroll
             for (int c = 0; c < 4; ++c) rq[c] = in_range_pos(qp[c], eps, 1000.0f) ? rcp_approx(qp[c]) : 0.f;
             const size_t o = ((size_t)b * H1 + (by * 4 + (r >> 1))) * W1 + bx * 4;
-            *reinterpret_cast<float4*>(py.lp[0] + o) = make_float4(a0.x, a0.y, a1.x, a1.y);
-            *reinterpret_cast<float4*>(py.lg[0] + o) = make_float4(b0.x, b0.y, b1.x, b1.y);
-            *reinterpret_cast<float4*>(py.rq[0] + o) = make_float4(rq[0], rq[1], rq[2], rq[3]);
+            if (act) {
+                *reinterpret_cast<float4*>(py.lp[0] + o) = make_float4(a0.x, a0.y, a1.x, a1.y);
+                *reinterpret_cast<float4*>(py.lg[0] + o) = make_float4(b0.x, b0.y, b1.x, b1.y);
+                *reinterpret_cast<float4*>(py.rq[0] + o) = make_float4(rq[0], rq[1], rq[2], rq[3]);
+            }
         }
         if ((r & 3) == 3) {   // a row of 2 scale-2 cells
             const float q0 = s2p[0] * 0.0625f, q1 = s2p[1] * 0.0625f, g0 = s2g[0] * 0.0625f, g1 = s2g[1] * 0.0625f;
             const float2 a = log_exact2(make_float2(clamp_nan(q0, eps, 1000.0f), clamp_nan(q1, eps, 1000.0f)));
             const float2 c = log_exact2(make_float2(clamp_nan(g0, eps, 1000.0f), clamp_nan(g1, eps, 1000.0f)));
             const size_t o = ((size_t)b * H2 + (by * 2 + (r >> 2))) * W2 + bx * 2;
-            *reinterpret_cast<float2*>(py.lp[1] + o) = a;
-            *reinterpret_cast<float2*>(py.lg[1] + o) = c;
-            *reinterpret_cast<float2*>(py.rq[1] + o) = make_float2(in_range_pos(q0, eps, 1000.0f) ? rcp_approx(q0) : 0.f,
-                                                                   in_range_pos(q1, eps, 1000.0f) ? rcp_approx(q1) : 0.f);
+            if (act) {
+                *reinterpret_cast<float2*>(py.lp[1] + o) = a;
+                *reinterpret_cast<float2*>(py.lg[1] + o) = c;
+                *reinterpret_cast<float2*>(py.rq[1] + o) = make_float2(in_range_pos(q0, eps, 1000.0f) ? rcp_approx(q0) : 0.f,
+                                                                       in_range_pos(q1, eps, 1000.0f) ? rcp_approx(q1) : 0.f);
+            }
         }
     }
     {
         const float q = s3p * 0.015625f, g = s3g * 0.015625f;
         const float2 l = log_exact2(make_float2(clamp_nan(q, eps, 1000.0f), clamp_nan(g, eps, 1000.0f)));
         const size_t o = ((size_t)b * H3 + by) * W3 + bx;
-        py.lp[2][o] = l.x;
-        py.lg[2][o] = l.y;
-        py.rq[2][o] = in_range_pos(q, eps, 1000.0f) ? rcp_approx(q) : 0.f;
+        if (act) {
+            py.lp[2][o] = l.x;
+            py.lg[2][o] = l.y;
+            py.rq[2][o] = in_range_pos(q, eps, 1000.0f) ? rcp_approx(q) : 0.f;
+        }
+    }
+    if constexpr ((SF & PS_PSUM) != 0) {
+        // this block's sum(pred) -> its image's fixed-point words: one pair of atomics per warp when the 32 blocks lie in
+        // one image (almost always), else per lane.  Integer atomics: any order, same bits.
+        const int b0 = __shfl_sync(0xffffffffu, b, 0);
+        float v = act ? bsum : 0.f;
+        const bool together = __all_sync(0xffffffffu, b == b0);
+        if (together) v = warp_sum(v);
+        if (together ? lane == 0 : act) {
+            unsigned long long hi, lo;
+            unsigned fl = 0u;
+            fix_split_signed((double)v, hi, lo, fl, 0);
+            unsigned long long* w = ps.img_words + 4 * (size_t)b;
+            if (hi) atomicAdd(w, hi);
+            if (lo) atomicAdd(w + 1, lo);
+            if (fl) atomicOr(reinterpret_cast<unsigned*>(w + 2), fl);
+        }
     }
     }   // blocks
     pdl_wait();
+    // the streaming kernel's per-image records (their offset depends on the shape, and one workspace serves calls of
+    // different shapes: what lies there may be another shape's partial sums) and pyr_coef_kernel's totals behind them
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < (B + 1) * 32; i += blockDim.x) img_rec_words[i] = 0u;      // 128 bytes each
+    if constexpr (SF != 0) {
+        __shared__ float s_w[8][2];
+        __shared__ unsigned s_n[8];
+        __shared__ int s_last;
+        const int warp = threadIdx.x >> 5;
+        if constexpr ((SF & PS_SI) != 0) {
+            const unsigned n = warp_sum(si_n);
+            const float s1 = warp_sum(si_s), q1 = warp_sum(si_q);
+            if (lane == 0) { s_n[warp] = n; s_w[warp][0] = s1; s_w[warp][1] = q1; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long n8 = 0ull;
+                for (int w = 0; w < 8; ++w) n8 += s_n[w];
+                if (n8) atomicAdd(&ps.rec->n, n8);
+            } else if (threadIdx.x == 32 || threadIdx.x == 64) {
+                const int q = threadIdx.x == 32 ? 0 : 1;
+                double t = 0.0;
+                for (int w = 0; w < 8; ++w) t += (double)s_w[w][q];
+                unsigned long long hi, lo;
+                unsigned fl = 0u;
+                fix_split_signed(t, hi, lo, fl, q);
+                if (hi) atomicAdd(q ? &ps.rec->q_hi : &ps.rec->s_hi, hi);
+                if (lo) atomicAdd(q ? &ps.rec->q_lo : &ps.rec->s_lo, lo);
+                if (fl) atomicOr(&ps.rec->flags, fl);
+            }
+        }
+        // ticket: the last CTA turns the fixed-point words into the doubles the gradient pass reads, and leaves them zero
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(&ps.rec->ticket, 1u) == gridDim.x - 1u;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            if constexpr ((SF & PS_SI) != 0) {
+                if (threadIdx.x == 0) {
+                    const unsigned fl = __ldcg(&ps.rec->flags);
+                    const double n = (double)__ldcg(&ps.rec->n);
+                    const double S = fix_join_signed(__ldcg(&ps.rec->s_hi), __ldcg(&ps.rec->s_lo), fl, 0);
+                    const double Q = fix_join_signed(__ldcg(&ps.rec->q_hi), __ldcg(&ps.rec->q_lo), fl, 1);
+                    ps.stats[ST_SI_N] = n;
+                    ps.stats[ST_SI_S] = S * 0.69314718055994531;                          // log2 -> natural units
+                    ps.stats[ST_SI_Q] = Q * (0.69314718055994531 * 0.69314718055994531);
+                    if (ps.want_rp) ps.stats[ST_RP_N] = n;
+                    ps.rec->n = 0ull; ps.rec->s_hi = 0ull; ps.rec->s_lo = 0ull; ps.rec->q_hi = 0ull; ps.rec->q_lo = 0ull;
+                    ps.rec->flags = 0u;
+                }
+            }
+            if constexpr ((SF & PS_PSUM) != 0) {
+                for (int i = threadIdx.x; i < B; i += blockDim.x) {
+                    unsigned long long* w = ps.img_words + 4 * (size_t)i;
+                    const unsigned fl = __ldcg(reinterpret_cast<const unsigned*>(w + 2));
+                    ps.img_psum[i] = fix_join_signed(__ldcg(w), __ldcg(w + 1), fl, 0);
+                    w[0] = 0ull; w[1] = 0ull; w[2] = 0ull;
+                }
+            }
+            if (threadIdx.x == 0) ps.rec->ticket = 0u;
+        }
+    }
 }
 
 // ================================================================================================
@@ -191,8 +335,7 @@ struct PyrCoefArgs {
     int B, H, W;
     float inv_nx[4], inv_ny[4];
     float wg;           // w_grad * upstream / num_scales
-    double* b_part;     // partial rows (BF_COUNT doubles each)
-    int row0;           // first row this kernel writes
+    unsigned long long* rec;   // fixed-point totals hi[6], lo[6], flags (zeroed by pyr_pool_kernel): GX1, GY1, GX2, GY2, GX3, GY3
 };
 
 __global__ void __launch_bounds__(256, CADL_PYR_MINB) pyr_coef_kernel(const PyrCoefArgs a) {
@@ -240,12 +383,18 @@ __global__ void __launch_bounds__(256, CADL_PYR_MINB) pyr_coef_kernel(const PyrC
         if (lane == 0) s_f[warp][q] = v;
     }
     __syncthreads();
-    if (threadIdx.x < BF_COUNT) {
+    if (threadIdx.x < 6) {
+        // this CTA's sums -> the totals, as fixed-point integer atomics: any order gives the same bits, and the
+        // gradient pass reads one record instead of folding a row per CTA
         const int q = threadIdx.x;
         double t = 0.0;
-        if (q >= BF_GX1 && q <= BF_GY3)
-            for (int w = 0; w < 8; ++w) t += (double)s_f[w][q - BF_GX1];
-        a.b_part[(size_t)(a.row0 + blockIdx.x) * BF_COUNT + q] = t;
+        for (int w = 0; w < 8; ++w) t += (double)s_f[w][q];
+        unsigned long long hi, lo;
+        unsigned fl = 0u;
+        fix_split(t, hi, lo, fl, q);
+        if (hi) atomicAdd(a.rec + q, hi);
+        if (lo) atomicAdd(a.rec + 6 + q, lo);
+        if (fl) atomicOr(reinterpret_cast<unsigned*>(a.rec + 12), fl);
     }
 }
 

@@ -27,12 +27,12 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 // (W, H, planes) fp32 tensor, box = (kS3BoxW, 1, 1), zero fill outside
-bool make_row_map(CUtensorMap* m, const float* base, int planes, int H, int W, int box_w = kS3BoxW) {
+bool make_row_map(CUtensorMap* m, const float* base, int planes, int H, int W, int box_w = kS3BoxW, int box_d = 1) {
     EncodeTiledFn fn = encode_fn();
     if (!fn || !base) return false;
     cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
     cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
-    cuuint32_t box[3] = {(cuuint32_t)box_w, 1, 1};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, 1, (cuuint32_t)box_d};
     cuuint32_t estr[3] = {1, 1, 1};
     return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -54,7 +54,7 @@ Geometry g_geo[16][16][2];   // [device][F][mask]
 template <int F, bool M>
 cudaError_t launch_one(const PhaseBArgs& a, Stream3Args& sa, cudaStream_t st) {
     constexpr bool SMOOTH = (F & FB_SMOOTH) != 0;
-    constexpr int SLOT = (SMOOTH ? 5 : 2) * kS3RowFloats + kS3C1Floats;
+    constexpr int SLOT = 2 * kS3RowFloats + (SMOOTH ? kS3RgbFloats : 0) + kS3C1Floats;
     constexpr int wpc = kS3Threads / 32;
     constexpr size_t smem = (size_t)wpc * kS3Depth * SLOT * sizeof(float);
     int dev = 0;
@@ -76,7 +76,7 @@ cudaError_t launch_one(const PhaseBArgs& a, Stream3Args& sa, cudaStream_t st) {
     RowMaps& tm = g_maps;
     if (!(tm.ok && tm.pp == a.pred && tm.pg == a.gt && tm.pi == (SMOOTH ? a.rgb : nullptr) && tm.pc == sa.c1 && tm.B == a.B && tm.H == a.H && tm.W == a.W)) {
         tm.ok = make_row_map(&tm.pred, a.pred, a.B, a.H, a.W) && make_row_map(&tm.gt, a.gt, a.B, a.H, a.W);
-        if (SMOOTH) tm.ok = tm.ok && make_row_map(&tm.rgb, a.rgb, 3 * a.B, a.H, a.W);
+        if (SMOOTH) tm.ok = tm.ok && make_row_map(&tm.rgb, a.rgb, 3 * a.B, a.H, a.W, kS3BoxW, kS3RgbDepth);
         else tm.rgb = tm.pred;
         tm.ok = tm.ok && make_row_map(&tm.c1, sa.c1, a.B, a.H / 2, a.W / 2, kS3C1BoxW);
         tm.pp = a.pred; tm.pg = a.gt; tm.pi = SMOOTH ? a.rgb : nullptr; tm.pc = sa.c1; tm.B = a.B; tm.H = a.H; tm.W = a.W;
@@ -122,3 +122,10 @@ bool stream3_fill_smooth(const PhaseBArgs& a, Stream3Args& sa) {
 }
 
 }  // namespace cadl
+
+#ifdef CADL_S3_TRACE
+extern "C" int cadl_debug_s3_trace(unsigned long long* out_host, int warps) {
+    if (warps > 4096) warps = 4096;
+    return (int)cudaMemcpyFromSymbol(out_host, cadl::g_s3_trace, sizeof(unsigned long long) * cadl::kS3TraceWords * (size_t)warps);
+}
+#endif

@@ -49,21 +49,6 @@ __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y
 // sign with NaN passed through (the exact tier)
 __device__ __forceinline__ float sgn3n(float x) { return (x != x) ? x : sgn3(x); }
 
-// value (>= 0) -> the two fixed-point words; non-finite or huge values are flagged instead
-__device__ __forceinline__ void fix_split(double v, unsigned long long& hi, unsigned long long& lo, unsigned& flag, int q) {
-    hi = 0ull; lo = 0ull;
-    if (!(v < 1.0e14)) { flag |= (v != v) ? (1u << q) : (1u << (8 + q)); return; }
-    if (!(v > 0.0)) return;
-    const double h = floor(v * 65536.0);
-    hi = (unsigned long long)h;
-    lo = (unsigned long long)__double2ll_rn((v - h * (1.0 / 65536.0)) * 72057594037927936.0);   // 2^56
-}
-__device__ __forceinline__ double fix_join(unsigned long long hi, unsigned long long lo, unsigned flags, int q) {
-    if (flags & (1u << q)) return __longlong_as_double(0x7ff8000000000000ll);
-    if (flags & (1u << (8 + q))) return __longlong_as_double(0x7ff0000000000000ll);
-    return (double)hi * (1.0 / 65536.0) + (double)lo * (1.0 / 72057594037927936.0);
-}
-
 // one lane of a converged warp (the compiler then knows the guarded block runs on exactly one thread: TMA operands
 // go straight to uniform registers instead of a per-active-lane loop)
 __device__ __forceinline__ bool elect_one() {
@@ -102,6 +87,17 @@ __device__ __forceinline__ void mbar_wait_parity(unsigned long long* bar, unsign
             else if (t - t0 > kS3WaitLimitNs) s3_bail(r, 1, warp, detail);
         }
     } while (!done);
+}
+
+// one probe, no loop: lets the step ask for the NEXT row's slot at its top (the answer travels through the MIO queue like
+// a shared-memory load) and only branch on it where the row is needed
+__device__ __forceinline__ unsigned mbar_test_parity(unsigned long long* bar, unsigned parity) {
+    unsigned done;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done;
 }
 
 // ---- the exact tier, out of line (rare: keeps the row loop short and its register budget for the common path) ----
@@ -143,6 +139,31 @@ __device__ __noinline__ float4 div4_ieee(float a, float b, float c, float d, flo
     return make_float4(__fdiv_rn(a, den), __fdiv_rn(b, den), __fdiv_rn(c, den), __fdiv_rn(d, den));
 }
 
+#ifdef CADL_S3_TRACE
+// tuning builds only (profiles/r02_trace.py): per warp {start, main loop done, image ready seen, end} in globaltimer ns,
+// rows whose slot was not ready when probed, and the time spent blocked on them
+constexpr int kS3TraceWords = 8;
+__device__ unsigned long long g_s3_trace[kS3TraceWords * 4096];
+#endif
+
+// Share `item` of the one-wave partition: image, 128-column strip, rows [ys, ye).  Items are numbered row range first
+// (item = kk * columns + column): the four warps of a CTA work on neighbouring strips of the same rows.
+// (Measured, not adopted: row ranges cut longer for the CTAs dispatched first to an SM, whose warps the schedulers
+//  favour -- 44 / 46 / 51 us mean loop time by dispatch rank with equal ranges, 46 / 47 / 49 with ranges 1.07 : 1.01 :
+//  0.92, but the slowest warp of every image still ends at 53-55 us and the kernel time does not move.)
+struct Share3 { int b, strip, ys, ye; };
+__device__ __forceinline__ int s3_row_bound(int k, int H, const Stream3Args& sa) {
+    return (int)((long long)H * k / sa.kpi);
+}
+__device__ __forceinline__ Share3 s3_share(int item, int B, int H, const Stream3Args& sa) {
+    const int ncols = B * sa.nstrip;
+    const int kk = item / ncols, col = item - kk * ncols;
+    Share3 s;
+    s.b = col / sa.nstrip; s.strip = col - s.b * sa.nstrip;
+    s.ys = s3_row_bound(kk, H, sa); s.ye = s3_row_bound(kk + 1, H, sa);
+    return s;
+}
+
 // One image row as a lane holds it in registers.
 struct Row3 {
     float4 p, g;        // pred, gt (4 adjacent pixels)
@@ -161,7 +182,11 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
     constexpr bool RP = (F & FB_RP) != 0;
     static_assert((F & FB_GRAD) != 0, "the streaming kernel is the gradient-matching path");
     constexpr int NI = SMOOTH ? 5 : 2;                       // image tensors streamed: pred, gt, 3 x rgb
-    constexpr int SLOT = NI * kS3RowFloats + kS3C1Floats;    // floats per ring slot: the image rows + the coarse-scale field C1 (half resolution)
+    // floats per ring slot: pred, gt (pitch kS3RowFloats), the three rgb rows (one box of depth 3: dense, pitch kS3BoxW)
+    // and the coarse-scale field C1 (half resolution); every array starts on TMA's 128-byte alignment
+    constexpr int RGB0 = 2 * kS3RowFloats, RGBP = kS3RgbPitch;
+    constexpr int C1OFF = RGB0 + (SMOOTH ? kS3RgbFloats : 0);
+    constexpr int SLOT = C1OFF + kS3C1Floats;
     constexpr int D = kS3Depth;
     extern __shared__ __align__(128) unsigned char s3_smem[];
     __shared__ __align__(8) unsigned long long s_bar[kS3Threads / 32][D];
@@ -187,6 +212,9 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
     unsigned ph = 0u;                                        // phase parity per slot
 
     pdl_wait();        // C1 of pyr_coef_kernel, the statistics of phase A
+#ifdef CADL_S3_TRACE
+    unsigned long long tr_t0 = gtime_ns(), tr_main = 0, tr_ready = 0, tr_blocked = 0, tr_late = 0;
+#endif
     // "image complete" is signalled as ready == epoch: nothing has to be reset while other warps may still poll it
     const unsigned epoch = __ldcg(sa.epoch) + 1u;
     // scalars derived from the phase-A statistics, weights and upstream folded in; d is in log2 units
@@ -205,9 +233,8 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
     const int nitems = a.B * spi;
 
     for (int item = gwarp; item < nitems; item += sa.nwarps) {
-        const int b = item / spi, r_ = item - b * spi;
-        const int strip = r_ / sa.kpi, kk = r_ - strip * sa.kpi;
-        const int ys = (int)((long long)H * kk / sa.kpi), ye = (int)((long long)H * (kk + 1) / sa.kpi);   // rows [ys, ye)
+        const Share3 sh = s3_share(item, a.B, H, sa);
+        const int b = sh.b, strip = sh.strip, ys = sh.ys, ye = sh.ye;                    // rows [ys, ye)
 
         const int img = b * plane;                           // B*H*W < 2^31 (checked on the host)
         float ab = 0.f;
@@ -254,13 +281,17 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
             mbar_expect_tx(bars + s, NI * kS3BoxBytes);
 #else
             mbar_expect_tx(bars + s, NI * kS3BoxBytes + kS3C1BoxBytes);
-            tma_load_3d(dst + NI * kS3RowFloats, &tm_c1, (x0 >> 1) - 4, y >> 1, b, bars + s);
+            tma_load_3d(dst + C1OFF, &tm_c1, (x0 >> 1) - 4, y >> 1, b, bars + s);
 #endif
             tma_load_3d(dst, &tm_pred, x0 - 4, y, b, bars + s);
             tma_load_3d(dst + kS3RowFloats, &tm_gt, x0 - 4, y, b, bars + s);
             if constexpr (SMOOTH) {
+#ifdef CADL_S3_RGB3
 #pragma unroll
-                for (int c = 0; c < 3; ++c) tma_load_3d(dst + (2 + c) * kS3RowFloats, &tm_rgb, x0 - 4, y, 3 * b + c, bars + s);
+                for (int c = 0; c < 3; ++c) tma_load_3d(dst + RGB0 + c * RGBP, &tm_rgb, x0 - 4, y, 3 * b + c, bars + s);
+#else
+                tma_load_3d(dst + RGB0, &tm_rgb, x0 - 4, y, 3 * b, bars + s);      // the three channel rows in one box
+#endif
             }
         };
         auto wait_slot = [&](int s) {
@@ -310,8 +341,8 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
                     float2 s = make_float2(0.f, 0.f);
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        const float2 ci = *reinterpret_cast<const float2*>(cI + (2 + c) * kS3RowFloats + 2 * h);
-                        const float2 ni = *reinterpret_cast<const float2*>(nI + (2 + c) * kS3RowFloats + 2 * h);
+                        const float2 ci = *reinterpret_cast<const float2*>(cI + RGB0 + c * RGBP + 2 * h);
+                        const float2 ni = *reinterpret_cast<const float2*>(nI + RGB0 + c * RGBP + 2 * h);
                         const float2 di = __fadd2_rn(ni, neg2(ci));
                         s = __fadd2_rn(s, make_float2(fabsf(di.x), fabsf(di.y)));     // depth_loss.h:218-227
                     }
@@ -337,6 +368,10 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
             if (ic - 1 + D < nseq) {
                 if (elect_one()) issue(ic - 1 + D, sp);
             }
+#ifndef CADL_S3_LATEWAIT
+            // the next row's slot: probe now, look at the answer in 4. (normally it completed several rows ago)
+            const unsigned n_ready = mbar_test_parity(bars + sn, (ph >> sn) & 1u);
+#endif
             uchar4 mk4 = make_uchar4(0, 0, 0, 0);
             const int gxc = lane_in ? gx0 : W - 4;
             if constexpr (HAS_MASK) mk4 = __ldg(reinterpret_cast<const uchar4*>(a.mask + img + gy * W + gxc));
@@ -351,7 +386,7 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
 #ifdef CADL_S3_NO_C1TMA
             const float2 ccv = __ldg(reinterpret_cast<const float2*>(sa.c1 + (b * (H >> 1) * (W >> 1) + (gy >> 1) * (W >> 1) + (gxc >> 1))));
 #else
-            const float2 ccv = *reinterpret_cast<const float2*>(ring + sc * (SLOT) + NI * kS3RowFloats + 4 + 2 * lane);
+            const float2 ccv = *reinterpret_cast<const float2*>(ring + sc * (SLOT) + C1OFF + 4 + 2 * lane);
 #endif
             const float pr = cq[4], gr = cq[kS3RowFloats + 4];                 // right neighbour of the lane's last pixel
             const float pl = cq[-1], gl = cq[kS3RowFloats - 1];                // left neighbour of its first pixel
@@ -376,10 +411,10 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
                 float Ix[3][5], Il[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const float4 v = *reinterpret_cast<const float4*>(cq + (2 + c) * kS3RowFloats);
+                    const float4 v = *reinterpret_cast<const float4*>(cq + RGB0 + c * RGBP);
                     Ix[c][0] = v.x; Ix[c][1] = v.y; Ix[c][2] = v.z; Ix[c][3] = v.w;
-                    Ix[c][4] = cq[(2 + c) * kS3RowFloats + 4];
-                    Il[c] = cq[(2 + c) * kS3RowFloats - 1];
+                    Ix[c][4] = cq[RGB0 + c * RGBP + 4];
+                    Il[c] = cq[RGB0 + c * RGBP - 1];
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -398,6 +433,20 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
                     flag |= (lane == 0) & (dl != dl);
                 }
             }
+
+            // the left lane's last edge is this lane's first: shuffled here so that its latency hides behind the pointwise
+            // terms (the exact tier, rare, repeats it after its fix-up)
+            auto left_from_lane = [&]() {
+                const float sl = __shfl_up_sync(0xffffffffu, sx[4], 1);
+                if (lane != 0) sx[0] = sl;
+                if constexpr (SMOOTH) {
+                    const float tl = __shfl_up_sync(0xffffffffu, tx[4], 1);
+                    if (lane != 0) tx[0] = tl;
+                }
+            };
+#ifndef CADL_S3_LATESHFL
+            left_from_lane();
+#endif
 
             // 3. pointwise terms
             const bool um[4] = {mk4.x != 0, mk4.y != 0, mk4.z != 0, mk4.w != 0};
@@ -455,7 +504,20 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
             }
 
             // 4. the next row: wait for its slot, its log differences, the vertical edges
+#ifndef CADL_S3_LATEWAIT
+#ifdef CADL_S3_TRACE
+            if (__any_sync(0xffffffffu, !n_ready)) {
+                const unsigned long long w0 = gtime_ns();
+                wait_slot(sn);
+                tr_blocked += gtime_ns() - w0; ++tr_late;
+            } else ph ^= 1u << sn;
+#else
+            if (__any_sync(0xffffffffu, !n_ready)) wait_slot(sn);
+            else ph ^= 1u << sn;
+#endif
+#else
             wait_slot(sn);
+#endif
             read_row(sn, N);
             yedges(C, N, cq, myq + sn * (SLOT), sy_dn, ty_dn, flag);
 
@@ -473,17 +535,15 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < 4; ++k) ty_dn[k] = fabsf(ty_dn[k]) * x.ty[k];
                 }
+#ifndef CADL_S3_LATESHFL
+                left_from_lane();
+#endif
             }
 
-            // 6. the left lane's last edge, assembly and the 128-bit store
-            {
-                const float sl = __shfl_up_sync(0xffffffffu, sx[4], 1);
-                if (lane != 0) sx[0] = sl;
-            }
-            if constexpr (SMOOTH) {
-                const float tl = __shfl_up_sync(0xffffffffu, tx[4], 1);
-                if (lane != 0) tx[0] = tl;
-            }
+            // 6. assembly and the 128-bit store
+#ifdef CADL_S3_LATESHFL
+            left_from_lane();
+#endif
             float out[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -535,6 +595,9 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
             ic += 2;
         }
 
+#ifdef CADL_S3_TRACE
+        tr_main = gtime_ns();
+#endif
         // this share's sums -> the image's fixed-point accumulators (integer atomics: any order, same result)
         {
             float it_gx = 0.f, it_gy = 0.f, it_smx = 0.f, it_smy = 0.f, it_rp = 0.f;
@@ -595,11 +658,25 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
     // (before the offset pass: the results do not depend on it, and its reductions need not be waited for)
     if (gwarp >= sa.nwarps) return;
     __syncwarp();
-    int fin = 0;
-    if (lane == 0) fin = atomicAdd(sa.done, 1u) == (unsigned)sa.nwarps - 1u;
-    fin = __shfl_sync(0xffffffffu, fin, 0);
+    unsigned ticket = 0;
+    if (lane == 0) ticket = atomicAdd(sa.done, 1u);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    const bool fin = ticket == (unsigned)sa.nwarps - 1u;
+    // the metric results need phase A's statistics only: the FIRST warp to get here writes them (it would otherwise
+    // just wait for its image), not the last one
+    if (ticket == 0u && a.metrics) write_metric_results(a.stats, a.metrics, *a.results, lane);
     if (fin) {
         __threadfence();
+        // Every load of this block is issued before the first use: the block runs while the other warps pour their
+        // offset reductions into the L2, a round trip takes microseconds then, and a chain of dependent loads here
+        // was a ~20 us tail on the whole kernel (profiles/r02_trace.py).
+        const double stv = a.stats[lane];                    // ST_COUNT == 32: one statistic per lane
+        double pqv = 0.0;
+        {
+            const unsigned pfl = __ldcg(reinterpret_cast<const unsigned*>(sa.pyr_rec + 12));
+            const int q = lane < 6 ? lane : 0;
+            pqv = fix_join(__ldcg(sa.pyr_rec + q), __ldcg(sa.pyr_rec + 6 + q), pfl, q);      // lane q: pooled-scale sum q
+        }
         // fixed order: lane-strided over the images, fixed shuffle tree
         double tq[IQ_COUNT], tl = 0.0;
 #pragma unroll
@@ -628,17 +705,13 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
 #pragma unroll
         for (int q = 0; q < IQ_COUNT; ++q) tq[q] = warp_sum(tq[q]);
         tl = warp_sum(tl);
-        // loss sums of the pooled scales (pyr_coef_kernel's rows), fixed order again
+        // loss sums of the pooled scales: pyr_coef_kernel's fixed-point totals (one record, no rows to fold here)
         double pq[6];
 #pragma unroll
-        for (int q = 0; q < 6; ++q) pq[q] = 0.0;
-        for (int i = lane; i < sa.n_pyr_rows; i += 32) {
-#pragma unroll
-            for (int q = 0; q < 6; ++q) pq[q] += __ldcg(sa.pyr_rows + (size_t)i * BF_COUNT + BF_GX1 + q);
-        }
-#pragma unroll
-        for (int q = 0; q < 6; ++q) pq[q] = warp_sum(pq[q]);
-        const double* st = a.stats;
+        for (int q = 0; q < 6; ++q) pq[q] = __shfl_sync(0xffffffffu, pqv, q);
+        static_assert(ST_COUNT == 32, "one statistic per lane");
+        const double st_si_n = __shfl_sync(0xffffffffu, stv, ST_SI_N), st_si_s = __shfl_sync(0xffffffffu, stv, ST_SI_S);
+        const double st_si_q = __shfl_sync(0xffffffffu, stv, ST_SI_Q), st_rp_n = __shfl_sync(0xffffffffu, stv, ST_RP_N);
         if (lane == 0) {
             cadl_results& r = *a.results;
             // gradient matching: scale 0 from this kernel, scales 1..3 from pyr_coef_kernel     depth_loss.h:162-163
@@ -653,16 +726,16 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
             gm *= 0.25;
             double si = 0.0, rp = 0.0;
             if (SI) {                                                                         // depth_loss.h:58-63
-                const double n = st[ST_SI_N];
-                if (n > 0.0) si = st[ST_SI_Q] / n - (double)a.lambda * st[ST_SI_S] * st[ST_SI_S] / (n * n);
+                const double n = st_si_n;
+                if (n > 0.0) si = st_si_q / n - (double)a.lambda * st_si_s * st_si_s / (n * n);
             }
             if (RP) {                                                                         // depth_loss.h:323-330
-                const double n = st[ST_RP_N];
+                const double n = st_rp_n;
                 if (n > 0.0) rp = tq[IQ_RP] / n;
             }
             const double sm = SMOOTH ? tl : 0.0;
-            r.n_si = SI ? (int64_t)st[ST_SI_N] : 0;
-            r.n_reproj = RP ? (int64_t)st[ST_RP_N] : 0;
+            r.n_si = SI ? (int64_t)st_si_n : 0;
+            r.n_reproj = RP ? (int64_t)st_rp_n : 0;
             r.d_si = si; r.d_grad = gm; r.d_smooth = sm; r.d_reproj = rp;
             r.loss_si = (float)si; r.loss_grad = (float)gm; r.loss_smooth = (float)sm; r.loss_reproj = (float)rp;
             // depth_loss.h:427-430, in float like the reference's tensor arithmetic
@@ -676,26 +749,32 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
             *sa.done = 0u;
             *sa.epoch = epoch;
         }
-        if (a.metrics) write_metric_results(a.stats, a.metrics, *a.results, lane);
     }
 
     // ---- grad[rows this warp wrote] -= off[b], once the image's sums are complete (rows are L2-resident) ----
     if (SMOOTH && want_grad) {
         for (int item = gwarp; item < nitems; item += sa.nwarps) {
-            const int b = item / spi, r_ = item - b * spi;
-            const int strip = r_ / sa.kpi, kk = r_ - strip * sa.kpi;
-            const int ys = (int)((long long)H * kk / sa.kpi), ye = (int)((long long)H * (kk + 1) / sa.kpi);
+            const Share3 sh = s3_share(item, a.B, H, sa);
+            const int b = sh.b, strip = sh.strip, ys = sh.ys, ye = sh.ye;
             const ImgRec* rec = sa.img + b;
             unsigned rdy = 0, spins = 0;
             unsigned long long t0 = 0;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(rdy) : "l"(&rec->ready) : "memory");
-                if (rdy != epoch && (++spins & 255u) == 0u) {
+            // relaxed polls with a pause (an acquire load invalidates the L1 on every probe and a busy loop takes issue
+            // slots from the warps of this SM that are still working); one acquire fence once the flag is seen
+            for (;;) {
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(rdy) : "l"(&rec->ready) : "memory");
+                if (rdy == epoch) break;
+                __nanosleep(256);
+                if ((++spins & 63u) == 0u) {
                     const unsigned long long t = gtime_ns();
                     if (t0 == 0) t0 = t;
                     else if (t - t0 > kS3WaitLimitNs) s3_bail(a.results, 2, gwarp, b);
                 }
-            } while (rdy != epoch);
+            }
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#ifdef CADL_S3_TRACE
+            tr_ready = gtime_ns();
+#endif
             float off;
             asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(off) : "l"(&rec->off) : "memory");
             // grad -= off as vector reductions executed at the L2 (same single fp32 rounding as a subtraction): nothing
@@ -703,16 +782,23 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
             const float noff = -off;
             const int gx0 = strip * 128 + 4 * lane;
             if (gx0 < W) {
-                // (four independent address registers per trip: a reduction holds its address until it has left the SM)
+                // (independent address registers: a reduction holds its address register until it has left the SM, so
+                //  a pointer that is bumped between two reductions stalls on the scoreboard; 43 rows -> 5 trips of 8)
                 float* gp = a.grad + (b * plane + ys * W + gx0);
                 int y = ys;
-                for (; y + 4 <= ye; y += 4) {
-                    float* g0 = gp; float* g1 = gp + W; float* g2 = gp + 2 * W; float* g3 = gp + 3 * W;
+                const size_t w1 = (size_t)W;
+                for (; y + 8 <= ye; y += 8) {
+                    float* g0 = gp; float* g1 = gp + w1; float* g2 = gp + 2 * w1; float* g3 = gp + 3 * w1;
+                    float* g4 = gp + 4 * w1; float* g5 = gp + 5 * w1; float* g6 = gp + 6 * w1; float* g7 = gp + 7 * w1;
                     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %1, %1, %1};" :: "l"(g0), "f"(noff) : "memory");
                     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %1, %1, %1};" :: "l"(g1), "f"(noff) : "memory");
                     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %1, %1, %1};" :: "l"(g2), "f"(noff) : "memory");
                     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %1, %1, %1};" :: "l"(g3), "f"(noff) : "memory");
-                    gp += 4 * W;
+                    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %1, %1, %1};" :: "l"(g4), "f"(noff) : "memory");
+                    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %1, %1, %1};" :: "l"(g5), "f"(noff) : "memory");
+                    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %1, %1, %1};" :: "l"(g6), "f"(noff) : "memory");
+                    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %1, %1, %1};" :: "l"(g7), "f"(noff) : "memory");
+                    gp += 8 * w1;
                 }
                 for (; y < ye; ++y) {
                     asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %1, %1, %1};" :: "l"(gp), "f"(noff) : "memory");
@@ -721,6 +807,14 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
             }
         }
     }
+#ifdef CADL_S3_TRACE
+    if (lane == 0 && gwarp < 4096) {
+        unsigned long long* t = g_s3_trace + (size_t)gwarp * kS3TraceWords;
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        t[0] = tr_t0; t[1] = tr_main; t[2] = tr_ready; t[3] = gtime_ns(); t[4] = tr_late; t[5] = tr_blocked; t[6] = smid; t[7] = 0;
+    }
+#endif
 
 }
 

@@ -23,6 +23,14 @@ constexpr int kS3C1BoxW = 72;                    // cells per C1 box: 4 + 64 + 4
 constexpr int kS3C1BoxBytes = kS3C1BoxW * 4;
 constexpr int kS3C1Floats = 96;                  // slot pitch of the C1 row: 384 B
 constexpr int kS3RowFloats = 160;                // slot pitch of one tensor's row: 640 B, a multiple of TMA's 128-byte alignment
+#ifdef CADL_S3_RGB3
+constexpr int kS3RgbDepth = 1;                   // one box per channel row, each on its own 128-byte aligned pitch
+constexpr int kS3RgbPitch = kS3RowFloats;
+#else
+constexpr int kS3RgbDepth = 3;                   // ONE box (136 x 1 x 3) for the three channel rows: lands dense
+constexpr int kS3RgbPitch = kS3BoxW;
+#endif
+constexpr int kS3RgbFloats = (3 * kS3RgbPitch + 31) / 32 * 32;   // 416 (dense) or 480
 
 struct alignas(16) ImgRec {        // per image, zero between calls
     unsigned long long hi[5];      // fixed point, 2^-16 units:  GX0, GY0, SMX, SMY, RP_E of this image
@@ -39,8 +47,8 @@ enum { IQ_GX0 = 0, IQ_GY0, IQ_SMX, IQ_SMY, IQ_RP, IQ_COUNT };
 
 struct Stream3Args {
     const float* c1;          // coarse-scale field (B, H/2, W/2) of pyr_coef_kernel
-    const double* pyr_rows;   // pyr_coef_kernel's partial rows (BF_COUNT doubles each): loss sums of scales 1..3
-    int n_pyr_rows;
+    const unsigned long long* pyr_rec;   // pyr_coef_kernel's fixed-point totals (the record after the B image records:
+                                         // hi[6], lo[6], flags): loss sums of scales 1..3
     ImgRec* img;
     unsigned int* done;       // warps finished (returned to 0)
     unsigned int* epoch;      // calls completed on this workspace: the value of ImgRec::ready that means "this call"

@@ -102,7 +102,8 @@ const char* cadl_error_string(int code);
  * aligned fast path; 8 = fast path as ONE tile kernel (cadl_phase_b_fast.cuh) instead of the pyramid + streaming
  * kernels; together with 8: 2 = stage tiles with cp.async instead of TMA; 16 = no programmatic dependent launch;
  * 32 = the pooled-pyramid kernels in line on the caller's stream instead of beside phase A on the auxiliary stream;
- * 64 = reprojection alone with the separate count kernel instead of the single cooperative launch.  All variants must
+ * 64 = reprojection alone with the separate count kernel instead of the single cooperative launch; 128 = the loss
+ * statistics from phase A (the kernels of the split API) instead of the pooled-sum pass.  All variants must
  * produce the same values (tests/test_math_gpu.py).  Process-global.
  * cadl_debug_kernel_times: with enable != 0 every following cadl_stack_fwd_bwd call records a CUDA event after each of
  * its launches and SYNCHRONISES at the end.  Returns the number of intervals of the LAST timed call and copies up to

@@ -56,6 +56,18 @@ __global__ void selftest_div_kernel(unsigned lo, unsigned hi, float b, unsigned 
     }
     if (bad) atomicAdd(mism, bad);
 }
+// div_via_double against __fdiv_rn, for ANY divisor (the gradient pass takes it where Markstein's scheme is not safe)
+__global__ void selftest_div2_kernel(unsigned lo, unsigned hi, float b, unsigned long long* mism) {
+    const float rb = __frcp_rn(b);
+    unsigned long long bad = 0;
+    for (unsigned long long u = (unsigned long long)lo + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; u <= hi;
+         u += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((unsigned)u);
+        bad += (__float_as_uint(div_via_double(x, b, rb)) != __float_as_uint(__fdiv_rn(x, b)));
+        bad += (__float_as_uint(div_via_double(-x, b, rb)) != __float_as_uint(__fdiv_rn(-x, b)));
+    }
+    if (bad) atomicAdd(mism, bad);
+}
 }  // namespace cadl
 
 namespace {
@@ -945,6 +957,8 @@ int cadl_selftest(int which, uint32_t lo_bits, uint32_t hi_bits, float param, un
         selftest_div_kernel<<<148 * 8, 256, 0, st>>>(lo_bits, hi_bits, param, mismatches_dev);
     } else if (which == 2) {
         selftest_lg2_kernel<<<148 * 8, 256, 0, st>>>(lo_bits, hi_bits, param, mismatches_dev);
+    } else if (which == 3) {
+        selftest_div2_kernel<<<148 * 8, 256, 0, st>>>(lo_bits, hi_bits, param, mismatches_dev);
     } else return CADL_ERR_UNSUPPORTED;
     return cuda_rc(cudaGetLastError());
 }

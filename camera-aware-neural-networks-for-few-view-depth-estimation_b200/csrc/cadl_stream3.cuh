@@ -134,10 +134,6 @@ __device__ __noinline__ ExactSigns exact_tier(float4 cp4, float4 cg4, float pl, 
     o.tx[0] = SMOOTH ? sgn3n(cp[0] - pl) : 0.f;
     return o;
 }
-// IEEE quotients for a divisor Markstein's scheme does not cover (all-ones significand): never taken in practice
-__device__ __noinline__ float4 div4_ieee(float a, float b, float c, float d, float den) {
-    return make_float4(__fdiv_rn(a, den), __fdiv_rn(b, den), __fdiv_rn(c, den), __fdiv_rn(d, den));
-}
 
 #ifdef CADL_S3_TRACE
 // tuning builds only (profiles/r02_trace.py): per warp {start, main loop done, image ready seen, end} in globaltimer ns,
@@ -486,10 +482,13 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
                         q0 = __fmul2_rn(tpy, rfy2);        pY = __ffma2_rn(__ffma2_rn(neg2(q0), fye2, tpy), rfy2, q0);
                         q0 = __fmul2_rn(tgy, rfy2);        gY = __ffma2_rn(__ffma2_rn(neg2(q0), fye2, tgy), rfy2, q0);
                     } else {
-                        const float4 qx = div4_ieee(tpx.x, tpx.y, tgx.x, tgx.y, fxe);
-                        const float4 qy = div4_ieee(tpy.x, tpy.y, tgy.x, tgy.y, fye);
-                        pX = make_float2(qx.x, qx.y); gX = make_float2(qx.z, qx.w);
-                        pY = make_float2(qy.x, qy.y); gY = make_float2(qy.z, qy.w);
+                        // a divisor Markstein's scheme does not cover (all-ones significand; never in practice): the
+                        // quotient through double precision, correctly rounded too (see div_via_double) and without
+                        // a call -- a call on this cold path constrained the registers of the whole row
+                        pX = make_float2(div_via_double(tpx.x, fxe, rfx), div_via_double(tpx.y, fxe, rfx));
+                        gX = make_float2(div_via_double(tgx.x, fxe, rfx), div_via_double(tgx.y, fxe, rfx));
+                        pY = make_float2(div_via_double(tpy.x, fye, rfy), div_via_double(tpy.y, fye, rfy));
+                        gY = make_float2(div_via_double(tgy.x, fye, rfy), div_via_double(tgy.y, fye, rfy));
                     }
                     const float2 dX = __fadd2_rn(pX, neg2(gX)), dY = __fadd2_rn(pY, neg2(gY)), dZ = __fadd2_rn(pp, neg2(gg));
                     const float2 ss = __fadd2_rn(__ffma2_rn(dZ, dZ, __ffma2_rn(dY, dY, __fmul2_rn(dX, dX))), eps2);

@@ -114,7 +114,9 @@ int cadl_debug_kernel_times(int enable, float* ms_out, const char** names_out, i
 /* Test hook: counts (into *mismatches_dev, a device uint64 the caller zeroed) the inputs with bit pattern in
  * [lo_bits, hi_bits] for which a device-math replica differs from the CUDA library form.
  *   which 0: log replica (scalar and packed fp32x2) vs logf;  which 1: Markstein a/param vs IEEE division;
- *   which 2: lg2.approx.ftz vs log2 in fp64: counts the inputs whose absolute error exceeds `param`. */
+ *   which 2: lg2.approx.ftz vs log2 in fp64: counts the inputs whose absolute error exceeds `param`;
+ *   which 3: a/param through double precision (the gradient pass's path for divisors Markstein's scheme does not
+ *   cover) vs IEEE division, any divisor. */
 int cadl_selftest(int which, uint32_t lo_bits, uint32_t hi_bits, float param, unsigned long long* mismatches_dev,
                   cadl_stream_t stream);
 

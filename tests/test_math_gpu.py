@@ -40,6 +40,16 @@ def test_markstein_division_is_correctly_rounded(pkg, b):
     assert pkg.selftest(1, _bits(0.5), _bits(2048.0), float(np.float32(b) + np.float32(1e-6))) == 0
 
 
+@pytest.mark.parametrize("b_bits", [0x43FFFFFF, 0x447FFFFF, 0x3FFFFFFF, 0x4401B6E8, 0x3EAAAAAB, 0x45F78000])
+def test_division_through_double_is_correctly_rounded(pkg, b_bits):
+    """The gradient pass's quotient for divisors Markstein's scheme does not cover (all-ones significand: the first three
+    values) is the IEEE one as well -- and for ordinary divisors too."""
+    b = float(np.array([b_bits], dtype=np.uint32).view(np.float32)[0])
+    assert pkg.selftest(3, _bits(1e-4), _bits(1e5), b) == 0
+    assert pkg.selftest(3, _bits(1e-30), _bits(1e-25), b) == 0
+    assert pkg.selftest(3, _bits(1e30), _bits(3e38), b) == 0
+
+
 @pytest.mark.parametrize("shape", [(2, 48, 128), (3, 96, 160), (1, 240, 320), (2, 8, 8), (2, 56, 72)])
 @pytest.mark.parametrize("terms", ["all", "three", "grad", "smooth"])
 def test_fast_kernel_equals_generic_kernel(pkg, shape, terms):

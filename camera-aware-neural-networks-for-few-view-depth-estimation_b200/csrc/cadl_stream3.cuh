@@ -25,6 +25,7 @@
 // Cooperative launch: warps wait for other warps' image sums, so the grid must be co-resident.
 #pragma once
 #include <cuda.h>   // CUtensorMap (type only)
+#include <type_traits>
 #include "cadl_args.cuh"
 #include "cadl_stream3_host.h"
 
@@ -356,8 +357,12 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
         // One row: C is the current row (sequence element ic, complete in registers), N receives element ic + 1.
         // up: signed terms of the edges to the row above (from the previous step); dn: those to the row below.
         // sc: ring slot of the current row (element ic); the slot before it is free and takes element ic - 1 + D
-        auto step = [&](int ic, int sc, int gy, float gyf, Row3& C, Row3& N, const float (&sy_up)[4], const float (&ty_up)[4],
+        // mk: std::true_type when Markstein's division covers both divisors (always, in practice): a compile-time tag, the
+        // row loop exists twice
+        auto step = [&](auto mk, int ic, int sc, int gy, float gyf, Row3& C, Row3& N, const float (&sy_up)[4], const float (&ty_up)[4],
                         float (&sy_dn)[4], float (&ty_dn)[4]) {
+            constexpr bool MK = decltype(mk)::value;
+            (void)MK;
             // 1. the slot of element ic - 1 was last read in the previous step: refill it
             __syncwarp();
             const int sp = sc == 0 ? D - 1 : sc - 1, sn = sc == D - 1 ? 0 : sc + 1;
@@ -370,6 +375,7 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
 #endif
             uchar4 mk4 = make_uchar4(0, 0, 0, 0);
             const int gxc = lane_in ? gx0 : W - 4;
+            (void)gxc;
             if constexpr (HAS_MASK) mk4 = __ldg(reinterpret_cast<const uchar4*>(a.mask + img + gy * W + gxc));
             const float cp[4] = {C.p.x, C.p.y, C.p.z, C.p.w}, cg[4] = {C.g.x, C.g.y, C.g.z, C.g.w};
             bool flag = false;
@@ -387,6 +393,7 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
             const float pr = cq[4], gr = cq[kS3RowFloats + 4];                 // right neighbour of the lane's last pixel
             const float pl = cq[-1], gl = cq[kS3RowFloats - 1];                // left neighbour of its first pixel
             float sx[5], tx[5];
+            (void)tx;
             {
                 const float dr = lg2_approx(clamp_nan(pr, eps, 1000.0f)) - lg2_approx(clamp_nan(gr, eps, 1000.0f));
                 const float dx[5] = {C.d[0], C.d[1], C.d[2], C.d[3], dr};
@@ -475,7 +482,7 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
                     float2 pX, gX, pY, gY;
                     const float2 tpx = __fmul2_rn(ax, pp), tgx = __fmul2_rn(ax, gg);
                     const float2 tpy = __fmul2_rn(ay2, pp), tgy = __fmul2_rn(ay2, gg);
-                    if (mk_ok) {
+                    if constexpr (MK) {
                         // Markstein: q0 = t * rb, rem = t - q0 * b (exact), q = q0 + rem * rb = RN(t / b)
                         float2 q0 = __fmul2_rn(tpx, rfx2); pX = __ffma2_rn(__ffma2_rn(neg2(q0), fxe2, tpx), rfx2, q0);
                         q0 = __fmul2_rn(tgx, rfx2);        gX = __ffma2_rn(__ffma2_rn(neg2(q0), fxe2, tgx), rfx2, q0);
@@ -582,17 +589,25 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
             wait_slot(0);
             read_row(0, RA);                                 // first image row: no edge above
         }
-        // two rows per trip, the two row buffers and the two edge buffers trading places: no register copies
-        float gyf = (float)ys;
-        for (int gy = ys; gy < ye; gy += 2) {
-            step(ic, sc, gy, gyf, RA, RB, u0s, u0t, u1s, u1t);
-            if (gy + 1 >= ye) break;
-            sc = sc == D - 1 ? 0 : sc + 1;
-            step(ic + 1, sc, gy + 1, gyf + 1.f, RB, RA, u1s, u1t, u0s, u0t);
-            sc = sc == D - 1 ? 0 : sc + 1;
-            gyf += 2.f;
-            ic += 2;
-        }
+        // two rows per trip, the two row buffers and the two edge buffers trading places: no register copies.
+        // (Measured, not adopted: the ring slot as a compile-time tag with the loop unrolled over a whole turn of the ring
+        //  -- every shared-memory address an immediate -- 73.7 us with 4 slots / 4 rows per trip, 101 us with 5 / 10,
+        //  against 69.9: the two-row body is already 17 KB of code and the instruction cache decides.  One row per trip
+        //  with register copies: 72.2.)
+        auto rows = [&](auto mk) {
+            float gyf = (float)ys;
+            for (int gy = ys; gy < ye; gy += 2) {
+                step(mk, ic, sc, gy, gyf, RA, RB, u0s, u0t, u1s, u1t);
+                if (gy + 1 >= ye) break;
+                sc = sc == D - 1 ? 0 : sc + 1;
+                step(mk, ic + 1, sc, gy + 1, gyf + 1.f, RB, RA, u1s, u1t, u0s, u0t);
+                sc = sc == D - 1 ? 0 : sc + 1;
+                gyf += 2.f;
+                ic += 2;
+            }
+        };
+        if (mk_ok) rows(std::true_type{});
+        else rows(std::false_type{});
 
 #ifdef CADL_S3_TRACE
         tr_main = gtime_ns();

@@ -108,10 +108,15 @@ __device__ __forceinline__ unsigned mbar_test_parity(unsigned long long* bar, un
 struct ExactSigns {
     float sx[5], sy[4], tx[5], ty[4];
 };
+// cq / nq: this lane's quad of the current / next row inside their ring slots (pred at [0..3], the neighbours at [-1]
+// and [4], gt one row pitch further).  The rows are read again from shared memory: passing the ten registers by value
+// put a dozen argument moves in front of the branch of EVERY row.
 template <bool SMOOTH>
-__device__ __noinline__ ExactSigns exact_tier(float4 cp4, float4 cg4, float pl, float gl, float pr, float gr, float4 np4,
-                                              float4 ng4, float eps) {
+__device__ __noinline__ ExactSigns exact_tier(const float* cq, const float* nq, float eps) {
     ExactSigns o;
+    const float4 cp4 = *reinterpret_cast<const float4*>(cq), cg4 = *reinterpret_cast<const float4*>(cq + kS3RowFloats);
+    const float4 np4 = *reinterpret_cast<const float4*>(nq), ng4 = *reinterpret_cast<const float4*>(nq + kS3RowFloats);
+    const float pl = cq[-1], gl = cq[kS3RowFloats - 1], pr = cq[4], gr = cq[kS3RowFloats + 4];
     const float cp[4] = {cp4.x, cp4.y, cp4.z, cp4.w}, cg[4] = {cg4.x, cg4.y, cg4.z, cg4.w};
     const float np[4] = {np4.x, np4.y, np4.z, np4.w}, ng[4] = {ng4.x, ng4.y, ng4.z, ng4.w};
     float lp[5], lg[5];
@@ -511,16 +516,18 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
 
             // 4. the next row: wait for its slot, its log differences, the vertical edges
 #ifndef CADL_S3_LATEWAIT
-#ifdef CADL_S3_TRACE
+            // (a branch over a cold block, not an if / else: the phase bit flips either way)
+            const unsigned par_n = (ph >> sn) & 1u;
+            ph ^= 1u << sn;
             if (__any_sync(0xffffffffu, !n_ready)) {
+#ifdef CADL_S3_TRACE
                 const unsigned long long w0 = gtime_ns();
-                wait_slot(sn);
+                mbar_wait_parity(bars + sn, par_n, a.results, gwarp, sn);
                 tr_blocked += gtime_ns() - w0; ++tr_late;
-            } else ph ^= 1u << sn;
 #else
-            if (__any_sync(0xffffffffu, !n_ready)) wait_slot(sn);
-            else ph ^= 1u << sn;
+                mbar_wait_parity(bars + sn, par_n, a.results, gwarp, sn);
 #endif
+            }
 #else
             wait_slot(sn);
 #endif
@@ -529,7 +536,7 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
 
             // 5. exact tier, warp-uniform and rare (about 1 % of the warp-rows on BASELINE's data)
             if (__any_sync(0xffffffffu, flag)) {
-                const ExactSigns x = exact_tier<SMOOTH>(C.p, C.g, pl, gl, pr, gr, N.p, N.g, eps);
+                const ExactSigns x = exact_tier<SMOOTH>(cq, myq + sn * (SLOT), eps);
                 sx[0] = x.sx[0] * inxl;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) sx[j + 1] = x.sx[j + 1] * (j == 3 ? inx3 : inx0);
@@ -577,7 +584,7 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
             yedges(RB, RA, myq, myq + SLOT, u0s, u0t, flag);
             sg_gy = k_gy; sg_smy = k_smy;                    // that edge is counted by the share above
             if (__any_sync(0xffffffffu, flag)) {
-                const ExactSigns x = exact_tier<SMOOTH>(RB.p, RB.g, 1.f, 1.f, 1.f, 1.f, RA.p, RA.g, eps);
+                const ExactSigns x = exact_tier<SMOOTH>(myq, myq + SLOT, eps);      // (only its vertical signs are used)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     u0s[k] = x.sy[k] * iny0;

@@ -102,6 +102,13 @@ cudaError_t launch_one(const PhaseBArgs& a, Stream3Args& sa, cudaStream_t st) {
 cudaError_t launch_stream3(int F, const PhaseBArgs& a, Stream3Args& sa, cudaStream_t st) {
     sa.inx0 = a.inv_nx[0] * 0.25f * a.w_grad * a.upstream;
     sa.iny0 = a.inv_ny[0] * 0.25f * a.w_grad * a.upstream;
+    for (int s = 0; s < 4; ++s) {
+        const int Hs = a.H >> s, Ws = a.W >> s;
+        // (x / 0 of the reference's empty mean: the sum is 0 there, and 0 * inf is the same NaN)
+        sa.rnx[s] = 1.0 / ((double)a.global_B * Hs * (Ws - 1));
+        sa.rny[s] = 1.0 / ((double)a.global_B * (Hs - 1) * Ws);
+    }
+    sa.r_hw = 1.0 / ((double)a.H * a.W);
     const bool m = a.mask != nullptr;
     switch (F) {
         case 15: return m ? launch_one<15, true>(a, sa, st) : launch_one<15, false>(a, sa, st);

@@ -166,6 +166,17 @@ __device__ __forceinline__ Share3 s3_share(int item, int B, int H, const Stream3
     return s;
 }
 
+// smooth_image_share (cadl_args.cuh) with the divisions by shape constants turned into multiplications: it runs on
+// the chain between the last row and the end of the kernel (last warp of an image -> results block), where a double
+// division is ~0.15 us of pure latency
+__device__ __forceinline__ void smooth_share3(const PhaseBArgs& a, const Stream3Args& sa, int img, double sx, double sy,
+                                              double& Lb, float& off) {
+    const double mean = a.img_psum[img] * sa.r_hw;
+    const float ab = 1.0f / ((float)mean + a.eps_smooth);   // depth_loss.h:193
+    Lb = (double)ab * (sx * sa.rnx[0] + sy * sa.rny[0]);
+    off = (float)((double)a.upstream * a.w_smooth * ab * Lb * sa.r_hw);
+}
+
 // One image row as a lane holds it in registers.
 struct Row3 {
     float4 p, g;        // pred, gt (4 adjacent pixels)
@@ -216,6 +227,7 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
     pdl_wait();        // C1 of pyr_coef_kernel, the statistics of phase A
 #ifdef CADL_S3_TRACE
     unsigned long long tr_t0 = gtime_ns(), tr_main = 0, tr_ready = 0, tr_blocked = 0, tr_late = 0;
+    unsigned long long tr_c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
     // "image complete" is signalled as ready == epoch: nothing has to be reset while other warps may still poll it
     const unsigned epoch = __ldcg(sa.epoch) + 1u;
@@ -240,7 +252,7 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
 
         const int img = b * plane;                           // B*H*W < 2^31 (checked on the host)
         float ab = 0.f;
-        if (SMOOTH) ab = 1.0f / ((float)(a.img_psum[b] / ((double)H * W)) + a.eps_smooth);      // a_b (:192-193)
+        if (SMOOTH) ab = 1.0f / ((float)(a.img_psum[b] * sa.r_hw) + a.eps_smooth);              // a_b (:192-193)
         float fxe = 1.f, fye = 1.f, rfx = 1.f, rfy = 1.f, cxv = 0.f, cyv = 0.f;
         bool mk_ok = true;
         if constexpr (RP) {
@@ -653,22 +665,29 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
             }
             __threadfence();
             __syncwarp();
+#ifdef CADL_S3_TRACE
+            tr_c[0] = gtime_ns();
+#endif
             int last = 0;
             if (lane == 0) last = atomicAdd(&rec->cnt, 1u) == (unsigned)spi - 1u;
             last = __shfl_sync(0xffffffffu, last, 0);
+#ifdef CADL_S3_TRACE
+            tr_c[1] = gtime_ns();
+#endif
             if (last && SMOOTH) {
-                // the image is complete: its share of the smoothness loss and the gradient offset
-                __threadfence();
+                // the image is complete: its share of the smoothness loss and the gradient offset.
+                // (acquire side only -- an L1 invalidate; a full fence here waits for the SM's write queue, which the
+                //  other warps' offset reductions fill at this point of the kernel)
+                asm volatile("fence.acquire.gpu;" ::: "memory");
                 if (lane == 0) {
                     const unsigned fl = __ldcg(&rec->flags);
                     const double sx_ = fix_join(__ldcg(&rec->hi[IQ_SMX]), __ldcg(&rec->lo[IQ_SMX]), fl, IQ_SMX);
                     const double sy_ = fix_join(__ldcg(&rec->hi[IQ_SMY]), __ldcg(&rec->lo[IQ_SMY]), fl, IQ_SMY);
                     double Lb;
                     float off;
-                    smooth_image_share(a, b, sx_, sy_, Lb, off);
+                    smooth_share3(a, sa, b, sx_, sy_, Lb, off);
                     rec->Lb = Lb;
                     rec->off = off;
-                    __threadfence();
                     asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(&rec->ready), "r"(epoch) : "memory");
                 }
             }
@@ -679,15 +698,21 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
     // (before the offset pass: the results do not depend on it, and its reductions need not be waited for)
     if (gwarp >= sa.nwarps) return;
     __syncwarp();
+#ifdef CADL_S3_TRACE
+    tr_c[2] = gtime_ns();
+#endif
     unsigned ticket = 0;
     if (lane == 0) ticket = atomicAdd(sa.done, 1u);
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
+#ifdef CADL_S3_TRACE
+    tr_c[3] = gtime_ns();
+#endif
     const bool fin = ticket == (unsigned)sa.nwarps - 1u;
     // the metric results need phase A's statistics only: the FIRST warp to get here writes them (it would otherwise
     // just wait for its image), not the last one
     if (ticket == 0u && a.metrics) write_metric_results(a.stats, a.metrics, *a.results, lane);
     if (fin) {
-        __threadfence();
+        asm volatile("fence.acquire.gpu;" ::: "memory");      // (every warp fenced its sums before its ticket)
         // Every load of this block is issued before the first use: the block runs while the other warps pour their
         // offset reductions into the L2, a round trip takes microseconds then, and a chain of dependent loads here
         // was a ~20 us tail on the whole kernel (profiles/r02_trace.py).
@@ -711,7 +736,7 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
                 double Lb = __ldcg(&rec->Lb);
                 float off = __ldcg(&rec->off);
                 if (!want_grad) {      // forward only: nobody computed the shares yet (ready is not used)
-                    smooth_image_share(a, i, fix_join(__ldcg(&rec->hi[IQ_SMX]), __ldcg(&rec->lo[IQ_SMX]), fl, IQ_SMX),
+                    smooth_share3(a, sa, i, fix_join(__ldcg(&rec->hi[IQ_SMX]), __ldcg(&rec->lo[IQ_SMX]), fl, IQ_SMX),
                                        fix_join(__ldcg(&rec->hi[IQ_SMY]), __ldcg(&rec->lo[IQ_SMY]), fl, IQ_SMY), Lb, off);
                 }
                 a.img_sm[2 * i] = Lb;
@@ -723,9 +748,15 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
             for (int q = 0; q < IQ_COUNT; ++q) { rec->hi[q] = 0ull; rec->lo[q] = 0ull; }
             rec->cnt = 0u; rec->flags = 0u;          // (off, Lb, ready are overwritten / epoch-valued)
         }
+#ifdef CADL_S3_TRACE
+        tr_c[4] = gtime_ns();
+#endif
 #pragma unroll
         for (int q = 0; q < IQ_COUNT; ++q) tq[q] = warp_sum(tq[q]);
         tl = warp_sum(tl);
+#ifdef CADL_S3_TRACE
+        tr_c[5] = gtime_ns();
+#endif
         // loss sums of the pooled scales: pyr_coef_kernel's fixed-point totals (one record, no rows to fold here)
         double pq[6];
 #pragma unroll
@@ -736,19 +767,23 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
         if (lane == 0) {
             cadl_results& r = *a.results;
             // gradient matching: scale 0 from this kernel, scales 1..3 from pyr_coef_kernel     depth_loss.h:162-163
+            // (reciprocals of the shape constants from the host, one reciprocal per count: this block is the end of
+            //  the kernel's critical chain and eight dependent double divisions were 1.2 us of it)
             double gm = 0.0;
+#pragma unroll
             for (int s = 0; s < 4; ++s) {
-                const int Hs = H >> s, Ws = W >> s;
-                const double nx = (double)a.global_B * Hs * (Ws - 1), ny = (double)a.global_B * (Hs - 1) * Ws;
                 const double sx_ = s == 0 ? tq[IQ_GX0] : pq[2 * (s - 1)];
                 const double sy_ = s == 0 ? tq[IQ_GY0] : pq[2 * (s - 1) + 1];
-                gm += sx_ / nx + sy_ / ny;
+                gm += sx_ * sa.rnx[s] + sy_ * sa.rny[s];                                      // NaN where a scale has no edges (0 * inf)
             }
             gm *= 0.25;
             double si = 0.0, rp = 0.0;
             if (SI) {                                                                         // depth_loss.h:58-63
                 const double n = st_si_n;
-                if (n > 0.0) si = st_si_q / n - (double)a.lambda * st_si_s * st_si_s / (n * n);
+                if (n > 0.0) {
+                    const double rn = 1.0 / n, m = st_si_s * rn;
+                    si = st_si_q * rn - (double)a.lambda * m * m;
+                }
             }
             if (RP) {                                                                         // depth_loss.h:323-330
                 const double n = st_rp_n;
@@ -772,6 +807,16 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
         }
     }
 
+#ifdef CADL_S3_TRACE
+    if (fin) {
+        tr_c[6] = gtime_ns();
+        if (lane == 0) {
+            unsigned long long* t = g_s3_trace + (size_t)4095 * kS3TraceWords;
+            for (int q = 0; q < 7; ++q) t[q] = tr_c[q] - tr_main;
+            t[7] = tr_main - tr_t0;
+        }
+    }
+#endif
     // ---- grad[rows this warp wrote] -= off[b], once the image's sums are complete (rows are L2-resident) ----
     if (SMOOTH && want_grad) {
         for (int item = gwarp; item < nitems; item += sa.nwarps) {

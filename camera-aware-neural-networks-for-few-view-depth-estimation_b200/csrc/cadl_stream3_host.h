@@ -58,6 +58,8 @@ struct Stream3Args {
     float lsnx, lsny;         // log2(w_smooth * upstream / N_x), log2(w_smooth * upstream / N_y)
     double inv_snx, inv_sny;  // their inverses: back from the scaled sums to sum w|dp|
     float inx0, iny0;         // w_grad * upstream / (4 N_x), / (4 N_y) of scale 0           depth_loss.h:162-163
+    double rnx[4], rny[4];    // 1 / (global_B * Hs * (Ws - 1)), 1 / (global_B * (Hs - 1) * Ws) per scale; inf where a scale has no edges
+    double r_hw;              // 1 / (H * W)
 };
 
 // F = FB_* mask (15, 7 or FB_GRAD).  Fills the launch geometry of sa, encodes the tensor maps and launches

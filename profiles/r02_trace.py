@@ -66,3 +66,9 @@ for mode in ("in step", "alone"):
         print(f"warp {w} of its CTA: mean loop length {lens[gw % WPC == w].mean():6.1f} us")
     nsm = len(np.unique(sm))
     print(f"dispatch: rank == block // SMs for {(rank == cta // nsm).mean() * 100:.1f} % of the warps ({nsm} SMs)")
+    # the results block's warp: ns after the end of its row loop at which it (0) has its sums out and fenced, (1) has its
+    # image ticket, (2) reaches the global ticket, (3) has it, (4) has loaded every record, (5) has reduced them,
+    # (6) has written the results; (7) = length of its row loop
+    fo = np.zeros(8 * 4096, dtype=np.uint64)
+    lib.cadl_debug_s3_trace(fo.ctypes.data_as(C.POINTER(C.c_ulonglong)), 4096)
+    print("results warp chain (ns after its last row):", [int(x) for x in fo.reshape(4096, 8)[4095].astype(np.int64)])

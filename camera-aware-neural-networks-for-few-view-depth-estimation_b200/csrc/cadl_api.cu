@@ -653,7 +653,7 @@ int run_grad(const float* pred, const float* gt, const float* rgb, const float* 
         const int HW = H * W;
         const int vec = (HW % 4 == 0) && aligned(grad, 16);
         int bx = (HW / 4 + 255) / 256;
-        int cap = (148 * 8 + B - 1) / B;
+        int cap = (kGridCap + B - 1) / B;
         if (bx > cap) bx = cap;
         if (bx < 1) bx = 1;
         smooth_offset_kernel<<<dim3(bx, B), 256, 0, st>>>(grad, ws.img_off(), HW, vec);
@@ -926,7 +926,7 @@ int cadl_scale_grad(const float* grad_in, const float* upstream_dev, float* grad
     if (n == 0) return CADL_OK;
     const int vec = aligned(grad_in, 16) && aligned(grad_out, 16);
     size_t blocks = (n / 4 + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > kGridCap) blocks = kGridCap;
     if (blocks < 1) blocks = 1;
     scale_grad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(grad_in, upstream_dev, grad_out, n, vec);
     return cuda_rc(cudaGetLastError());
@@ -951,14 +951,14 @@ int cadl_selftest(int which, uint32_t lo_bits, uint32_t hi_bits, float param, un
     if (!mismatches_dev) return CADL_ERR_NULL;
     if (hi_bits < lo_bits) return CADL_ERR_SHAPE;
     cudaStream_t st = (cudaStream_t)stream;
-    if (which == 0) selftest_log_kernel<<<148 * 8, 256, 0, st>>>(lo_bits, hi_bits, mismatches_dev);
+    if (which == 0) selftest_log_kernel<<<kGridCap, 256, 0, st>>>(lo_bits, hi_bits, mismatches_dev);
     else if (which == 1) {
         if (!markstein_safe_host(param)) return CADL_ERR_UNSUPPORTED;
-        selftest_div_kernel<<<148 * 8, 256, 0, st>>>(lo_bits, hi_bits, param, mismatches_dev);
+        selftest_div_kernel<<<kGridCap, 256, 0, st>>>(lo_bits, hi_bits, param, mismatches_dev);
     } else if (which == 2) {
-        selftest_lg2_kernel<<<148 * 8, 256, 0, st>>>(lo_bits, hi_bits, param, mismatches_dev);
+        selftest_lg2_kernel<<<kGridCap, 256, 0, st>>>(lo_bits, hi_bits, param, mismatches_dev);
     } else if (which == 3) {
-        selftest_div2_kernel<<<148 * 8, 256, 0, st>>>(lo_bits, hi_bits, param, mismatches_dev);
+        selftest_div2_kernel<<<kGridCap, 256, 0, st>>>(lo_bits, hi_bits, param, mismatches_dev);
     } else return CADL_ERR_UNSUPPORTED;
     return cuda_rc(cudaGetLastError());
 }
@@ -1050,7 +1050,7 @@ int cadl_accumulate(const float* values_dev, int n, double weight, double* acc_d
     return cuda_rc(cudaGetLastError());
 }
 
-size_t cadl_clip_workspace_bytes(void) { return 256 + sizeof(double) * 148 * 8; }
+size_t cadl_clip_workspace_bytes(void) { return 256 + sizeof(double) * kGridCap; }
 
 int cadl_clip_grad_norm(float* const* grad_ptrs_dev, const long long* sizes_dev, const long long* chunk_prefix_dev,
                         int count, long long total_chunks, float max_norm, float* out2_dev, void* workspace,
@@ -1063,7 +1063,7 @@ int cadl_clip_grad_norm(float* const* grad_ptrs_dev, const long long* sizes_dev,
     a.max_norm = max_norm; a.out = out2_dev;
     a.hdr = reinterpret_cast<WsHeader*>(workspace);
     a.part = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
-    int grid = 148 * 8;
+    int grid = kGridCap;
     if ((long long)grid > total_chunks) grid = (int)total_chunks;
     a.part_rows = grid;
     cudaStream_t st = (cudaStream_t)stream;

@@ -59,7 +59,12 @@ struct WsLayout {
     int pyr_blocks;   // CTAs of pyr_pool_kernel / pyr_coef_kernel (0: shape not a multiple of 8)
 };
 
-constexpr int kPointBlocks = 148 * 8;       // partial rows of the pointwise kernels
+// Capacities of the partial-row arrays and caps of the grid-stride grids.  They are LAYOUT constants (the workspace size
+// must not depend on the device): sized for B200's 148 SMs x 8 CTAs; launch geometry that has to match the device
+// (resident waves, cooperative grids) queries the SM count and the occupancy instead.
+constexpr int kLayoutSms = 148;
+constexpr int kGridCap = kLayoutSms * 8;
+constexpr int kPointBlocks = kGridCap;      // partial rows of the pointwise kernels
 
 constexpr int kThreadsA = 256;
 constexpr int kThreadsB = 256;
@@ -72,7 +77,7 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 __host__ inline int a_blocks_per_image(int B, int HW) {
     // ~4 resident blocks per SM over 148 SMs in one wave (fat threads amortise the block-end reduction),
     // at least 1024 px per block, each block inside one image
-    int target = (148 * 4) / B;          // rounded DOWN: one block too many per image starts a second, almost empty wave
+    int target = (kLayoutSms * 4) / B;          // rounded DOWN: one block too many per image starts a second, almost empty wave
     if (target < 1) target = 1;
     int by_size = (HW + 1023) / 1024;
     int n = target < by_size ? target : by_size;

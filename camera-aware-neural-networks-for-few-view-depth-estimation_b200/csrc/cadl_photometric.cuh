@@ -169,7 +169,7 @@ inline cudaError_t launch_photometric(const float* pred, const float* K, int k_b
     const size_t n = (size_t)total;
     const int vec = (reinterpret_cast<uintptr_t>(grad) % 16) == 0;
     size_t sb = (n / 4 + 255) / 256;
-    if (sb > 148 * 8) sb = 148 * 8;
+    if (sb > (size_t)kGridCap) sb = kGridCap;
     if (sb < 1) sb = 1;
     // grad *= upstream / n  (same kernel as the autograd scale; scale_out lives in the workspace)
     scale_grad_kernel<<<(unsigned)sb, 256, 0, st>>>(grad, scale_out, grad, n, vec);

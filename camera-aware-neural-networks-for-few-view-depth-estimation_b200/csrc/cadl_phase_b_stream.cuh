@@ -338,7 +338,13 @@ struct PyrCoefArgs {
     unsigned long long* rec;   // fixed-point totals hi[6], lo[6], flags (zeroed by pyr_pool_kernel): GX1, GY1, GX2, GY2, GX3, GY3
 };
 
-__global__ void __launch_bounds__(256, CADL_PYR_MINB) pyr_coef_kernel(const PyrCoefArgs a) {
+// Latency-bound gathers: fewer, fatter threads win -- at 124 registers (2 CTAs per SM) the compiler keeps the loads of a
+// whole level in flight; the step without metrics 108.1 -> 106.0 us against the 64-register build (3 CTAs: 106.7),
+// with phase A beside it unchanged.
+#ifndef CADL_COEF_MINB
+#define CADL_COEF_MINB 2
+#endif
+__global__ void __launch_bounds__(256, CADL_COEF_MINB) pyr_coef_kernel(const PyrCoefArgs a) {
     __shared__ float s_f[8][6];
     pdl_wait();        // the pooled arrays of pyr_pool_kernel
     pdl_trigger();

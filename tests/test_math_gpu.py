@@ -40,6 +40,48 @@ def test_markstein_division_is_correctly_rounded(pkg, b):
     assert pkg.selftest(1, _bits(0.5), _bits(2048.0), float(np.float32(b) + np.float32(1e-6))) == 0
 
 
+@pytest.mark.parametrize("shape,masked", [((3, 40, 200), True),      # 375 blocks of 8x8: the last warp of the pooled-sum pass is partly idle
+                                          ((3, 40, 200), False),
+                                          ((5, 24, 384), True),      # warps that straddle two images
+                                          ((33, 8, 8), False),       # one block per image: every lane of a warp in another image
+                                          ((2, 64, 136), False),
+                                          ((1, 240, 320), True)])
+@pytest.mark.parametrize("terms", ["all", "three"])
+def test_loss_statistics_from_the_pooled_sum_pass(pkg, shape, masked, terms):
+    """Without metric variants the step has no phase A: SI n / sum d / sum d^2, the reprojection count and the per-image
+    sum(pred) come from the pooled-sum kernel (fixed-point integer atomics).  Against the layout that takes them from
+    phase A (debug mode 128) and against the generic kernel (mode 1), on shapes that stress its warp-uniform loop."""
+    B, H, W = shape
+    d = torch.device("cuda:0")
+    b = pkg.synth.make_batch(B, H, W, seed=7 * B + H + W, device=d)
+    mask = (torch.rand(B, 1, H, W, device=d) < 0.7) if masked else None
+    T = pkg.TERM_ALL if terms == "all" else (pkg.TERM_SI | pkg.TERM_GRAD | pkg.TERM_SMOOTH)
+    res = {}
+    for mode in (0, 128, 1):
+        pkg.force_generic(mode)
+        try:
+            ws = pkg.stack_fwd_bwd(b["pred"], b["gt"], b["rgb"], b["K"] if terms == "all" else None, mask,
+                                   params=pkg.default_params(terms=T, metrics=0))
+            torch.cuda.synchronize()
+            res[mode] = (pkg.results_dict(ws.read_results()), ws.grad.clone())
+        finally:
+            pkg.force_generic(0)
+    (r0, g0), (ra, ga), (rg, gg) = res[0], res[128], res[1]
+    assert r0["n_si"] == ra["n_si"] == rg["n_si"] and r0["n_reproj"] == ra["n_reproj"] == rg["n_reproj"]
+    for k in ("loss_total", "si_loss", "grad_loss", "smooth_loss", "reproj_loss"):
+        assert rel_err(r0[k], ra[k]) <= 2e-6, (k, r0[k], ra[k])
+        assert rel_err(r0[k], rg[k]) <= 2e-6, (k, r0[k], rg[k])
+    scale = float(gg.abs().max())
+    assert float((g0 - ga).abs().max()) <= 2e-6 * scale
+    assert float((g0 - gg).abs().max()) <= 2e-6 * scale
+    # twice the same call: bit-identical (integer atomics are order-free)
+    ws2 = pkg.stack_fwd_bwd(b["pred"], b["gt"], b["rgb"], b["K"] if terms == "all" else None, mask,
+                            params=pkg.default_params(terms=T, metrics=0))
+    torch.cuda.synchronize()
+    assert torch.equal(ws2.grad, g0)
+    assert rel_err(pkg.results_dict(ws2.read_results())["loss_total"], r0["loss_total"]) == 0.0      # NaN-aware (8x8)
+
+
 @pytest.mark.parametrize("b_bits", [0x43FFFFFF, 0x447FFFFF, 0x3FFFFFFF, 0x4401B6E8, 0x3EAAAAAB, 0x45F78000])
 def test_division_through_double_is_correctly_rounded(pkg, b_bits):
     """The gradient pass's quotient for divisors Markstein's scheme does not cover (all-ones significand: the first three

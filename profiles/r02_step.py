@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 pkg = importlib.import_module("camera-aware-neural-networks-for-few-view-depth-estimation_b200")
 dev = torch.device("cuda:0")
 tag = os.path.basename(os.environ.get("CADL_LIB", "libcadl.so"))
-B, H, W = 32, 480, 640
+B, H, W = int(os.environ.get("BATCH", "32")), 480, 640
 b = pkg.synth.make_batch(B, H, W, seed=1234, device=dev)
 ws = pkg.Workspace(B, H, W, dev)
 grad = torch.empty_like(b["pred"])

@@ -5,11 +5,15 @@
 
 namespace cadl {
 
+// One CTA of twelve warps per SM.  The same twelve warps as three CTAs of four (the register file holds no more at 166
+// registers), but warps of ONE CTA have the same age for the schedulers and progress evenly: with three CTAs the warps of
+// the first-dispatched one finish their rows at 40 us and those of the last at 47 (profiles/r02_trace.txt), and the SM's
+// last third runs under-occupied.  65.3 -> 63.8 us (4 x 96 threads and 2 x 192: 64.3).
 #ifndef CADL_S3_THREADS
-#define CADL_S3_THREADS 128
+#define CADL_S3_THREADS 384
 #endif
 #ifndef CADL_S3_MINB
-#define CADL_S3_MINB 3
+#define CADL_S3_MINB 1
 #endif
 #ifndef CADL_S3_DEPTH
 #define CADL_S3_DEPTH 5

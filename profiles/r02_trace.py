@@ -19,7 +19,7 @@ grad = torch.empty_like(b["pred"])
 params = pkg.default_params(metrics=3)
 lib = C.CDLL(os.environ["CADL_LIB"])
 NW = int(os.environ.get("NW", "1760"))
-WPC = int(os.environ.get("WPC", "4"))
+WPC = int(os.environ.get("WPC", "12"))
 for it in range(6):
     pkg.stack_fwd_bwd(b["pred"], b["gt"], b["rgb"], b["K"], None, params=params, grad=grad, ws=ws)
 torch.cuda.synchronize()

@@ -291,21 +291,12 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
             int y = r_first + i;
             y = y < H ? y : H - 1;
             float* dst = ring + (size_t)s * SLOT;
-#ifdef CADL_S3_NO_C1TMA
-            mbar_expect_tx(bars + s, NI * kS3BoxBytes);
-#else
             mbar_expect_tx(bars + s, NI * kS3BoxBytes + kS3C1BoxBytes);
             tma_load_3d(dst + C1OFF, &tm_c1, (x0 >> 1) - 4, y >> 1, b, bars + s);
-#endif
             tma_load_3d(dst, &tm_pred, x0 - 4, y, b, bars + s);
             tma_load_3d(dst + kS3RowFloats, &tm_gt, x0 - 4, y, b, bars + s);
             if constexpr (SMOOTH) {
-#ifdef CADL_S3_RGB3
-#pragma unroll
-                for (int c = 0; c < 3; ++c) tma_load_3d(dst + RGB0 + c * RGBP, &tm_rgb, x0 - 4, y, 3 * b + c, bars + s);
-#else
                 tma_load_3d(dst + RGB0, &tm_rgb, x0 - 4, y, 3 * b, bars + s);      // the three channel rows in one box
-#endif
             }
         };
         auto wait_slot = [&](int s) {
@@ -386,10 +377,8 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
             if (ic - 1 + D < nseq) {
                 if (elect_one()) issue(ic - 1 + D, sp);
             }
-#ifndef CADL_S3_LATEWAIT
             // the next row's slot: probe now, look at the answer in 4. (normally it completed several rows ago)
             const unsigned n_ready = mbar_test_parity(bars + sn, (ph >> sn) & 1u);
-#endif
             uchar4 mk4 = make_uchar4(0, 0, 0, 0);
             const int gxc = lane_in ? gx0 : W - 4;
             (void)gxc;
@@ -402,11 +391,7 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
             const float* cq = myq + sc * (SLOT);                  // the current row's slot: neighbours
             // the coarse-scale field of this row's 2x2 cells: element j of its array <-> cell column x0/2 - 4 + j
             // (the box starts 16-byte aligned like the image boxes: a start at x0/2 - 2 raised an illegal-instruction fault)
-#ifdef CADL_S3_NO_C1TMA
-            const float2 ccv = __ldg(reinterpret_cast<const float2*>(sa.c1 + (b * (H >> 1) * (W >> 1) + (gy >> 1) * (W >> 1) + (gxc >> 1))));
-#else
             const float2 ccv = *reinterpret_cast<const float2*>(ring + sc * (SLOT) + C1OFF + 4 + 2 * lane);
-#endif
             const float pr = cq[4], gr = cq[kS3RowFloats + 4];                 // right neighbour of the lane's last pixel
             const float pl = cq[-1], gl = cq[kS3RowFloats - 1];                // left neighbour of its first pixel
             float sx[5], tx[5];
@@ -464,9 +449,7 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
                     if (lane != 0) tx[0] = tl;
                 }
             };
-#ifndef CADL_S3_LATESHFL
             left_from_lane();
-#endif
 
             // 3. pointwise terms
             const bool um[4] = {mk4.x != 0, mk4.y != 0, mk4.z != 0, mk4.w != 0};
@@ -527,7 +510,6 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
             }
 
             // 4. the next row: wait for its slot, its log differences, the vertical edges
-#ifndef CADL_S3_LATEWAIT
             // (a branch over a cold block, not an if / else: the phase bit flips either way)
             const unsigned par_n = (ph >> sn) & 1u;
             ph ^= 1u << sn;
@@ -540,9 +522,6 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
                 mbar_wait_parity(bars + sn, par_n, a.results, gwarp, sn);
 #endif
             }
-#else
-            wait_slot(sn);
-#endif
             read_row(sn, N);
             yedges(C, N, cq, myq + sn * (SLOT), sy_dn, ty_dn, flag);
 
@@ -560,15 +539,10 @@ stream3_kernel(const PhaseBArgs a, const Stream3Args sa, const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < 4; ++k) ty_dn[k] = fabsf(ty_dn[k]) * x.ty[k];
                 }
-#ifndef CADL_S3_LATESHFL
                 left_from_lane();
-#endif
             }
 
             // 6. assembly and the 128-bit store
-#ifdef CADL_S3_LATESHFL
-            left_from_lane();
-#endif
             float out[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {

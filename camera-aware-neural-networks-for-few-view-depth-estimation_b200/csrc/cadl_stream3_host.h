@@ -27,13 +27,8 @@ constexpr int kS3C1BoxW = 72;                    // cells per C1 box: 4 + 64 + 4
 constexpr int kS3C1BoxBytes = kS3C1BoxW * 4;
 constexpr int kS3C1Floats = 96;                  // slot pitch of the C1 row: 384 B
 constexpr int kS3RowFloats = 160;                // slot pitch of one tensor's row: 640 B, a multiple of TMA's 128-byte alignment
-#ifdef CADL_S3_RGB3
-constexpr int kS3RgbDepth = 1;                   // one box per channel row, each on its own 128-byte aligned pitch
-constexpr int kS3RgbPitch = kS3RowFloats;
-#else
 constexpr int kS3RgbDepth = 3;                   // ONE box (136 x 1 x 3) for the three channel rows: lands dense
 constexpr int kS3RgbPitch = kS3BoxW;
-#endif
 constexpr int kS3RgbFloats = (3 * kS3RgbPitch + 31) / 32 * 32;   // 416 (dense) or 480
 
 struct alignas(16) ImgRec {        // per image, zero between calls
